@@ -1,0 +1,194 @@
+"""ctypes binding of ``libcircuitree_b200.so`` (the C ABI declared in include/circuitree_b200.h).
+
+This is the only module that touches the shared library.  There is no CPU fallback: if the
+library is missing or no CUDA device is present, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+from pathlib import Path
+from typing import Optional, Sequence
+
+import numpy as np
+
+N_PARAMS = 10
+MAX_SPECIES = 5
+MAX_NDEC = 126
+
+_LIB_PATH = Path(__file__).resolve().parent / "libcircuitree_b200.so"
+_lib: Optional[ctypes.CDLL] = None
+
+
+class EngineError(RuntimeError):
+    """Raised when a C-ABI call returns a non-zero status."""
+
+
+class SimConfig(ctypes.Structure):
+    """Mirror of ``ct_sim_config`` (SPEC.md sections 4-7)."""
+
+    _fields_ = [
+        ("nt", ctypes.c_int32),
+        ("decim", ctypes.c_int32),
+        ("dt", ctypes.c_float),
+        ("init_mean", ctypes.c_float),
+        ("ranges", (ctypes.c_float * 3) * N_PARAMS),
+    ]
+
+    def ranges_array(self) -> np.ndarray:
+        return np.array([[self.ranges[i][j] for j in range(3)] for i in range(N_PARAMS)], dtype=np.float64)
+
+    def set_ranges(self, ranges) -> None:
+        r = np.asarray(ranges, dtype=np.float32).reshape(N_PARAMS, 3)
+        for i in range(N_PARAMS):
+            for j in range(3):
+                self.ranges[i][j] = float(r[i, j])
+
+    @property
+    def n_dec(self) -> int:
+        return self.nt // self.decim
+
+
+def library_path() -> Path:
+    return _LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise EngineError(
+            f"{_LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  circuitree_b200 has no CPU fallback for the reward path."
+        )
+    L = ctypes.CDLL(str(_LIB_PATH))
+    vp, i32, u64, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint64, ctypes.c_int64
+    L.ct_last_error.restype = ctypes.c_char_p
+    L.ct_last_error.argtypes = []
+    L.ct_version.restype = ctypes.c_int
+    L.ct_default_config.argtypes = [ctypes.POINTER(SimConfig)]
+    L.ct_engine_create.argtypes = [ctypes.c_int, ctypes.POINTER(vp)]
+    L.ct_engine_destroy.argtypes = [vp]
+    L.ct_engine_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]
+    L.ct_compile_topology.argtypes = [i32, vp, i32, vp, i32, i32, ctypes.POINTER(u64)]
+    L.ct_launch_rewards.argtypes = [vp, vp, vp, vp, i32, ctypes.POINTER(SimConfig), u64, vp, vp, vp, vp, vp, vp, i32]
+    L.ct_reduce_jobs.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
+    L.ct_rewards_host.argtypes = [vp, vp, vp, vp, i32, ctypes.POINTER(SimConfig), u64, vp, vp, vp, vp, vp]
+    L.ct_reward_from_series_host.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    L.ct_engine_launch_count.restype = i64
+    L.ct_engine_launch_count.argtypes = [vp]
+    for name in ("ct_default_config", "ct_engine_create", "ct_engine_destroy", "ct_engine_info",
+                 "ct_compile_topology", "ct_launch_rewards", "ct_reduce_jobs", "ct_rewards_host",
+                 "ct_reward_from_series_host"):
+        getattr(L, name).restype = ctypes.c_int
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = lib().ct_last_error().decode("utf-8", "replace")
+        raise EngineError(f"circuitree_b200 C ABI error {rc}: {msg}")
+
+
+def default_config() -> SimConfig:
+    cfg = SimConfig()
+    check(lib().ct_default_config(ctypes.byref(cfg)))
+    return cfg
+
+
+def compile_topology(n_species: int, activations, inhibitions, k: int = 2) -> int:
+    """``parse_genotype`` arrays (reference models.py:441-480) -> 64-bit topology handle."""
+    act = np.ascontiguousarray(np.asarray(activations, dtype=np.int64).reshape(-1, k))
+    inh = np.ascontiguousarray(np.asarray(inhibitions, dtype=np.int64).reshape(-1, k))
+    h = ctypes.c_uint64(0)
+    check(lib().ct_compile_topology(n_species, act.ctypes.data, act.shape[0], inh.ctypes.data, inh.shape[0], k,
+                                    ctypes.byref(h)))
+    return int(h.value)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return int(a)
+
+
+class Engine:
+    """One engine per CUDA device (``ct_engine``)."""
+
+    def __init__(self, device: int = 0):
+        self._h = ctypes.c_void_p(None)
+        check(lib().ct_engine_create(device, ctypes.byref(self._h)))
+        self.device = device
+        n_sm, lanes = ctypes.c_int32(0), ctypes.c_int32(0)
+        check(lib().ct_engine_info(self._h, ctypes.byref(n_sm), ctypes.byref(lanes)))
+        self.n_sm = int(n_sm.value)
+        self.resident_lanes = int(lanes.value)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().ct_engine_destroy(self._h)
+            self._h = ctypes.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().ct_engine_launch_count(self._h))
+
+    # -- device-buffer path (torch tensors are only buffers: pass tensor.data_ptr()) --------------
+    def launch_rewards(self, handles: np.ndarray, n_traj: np.ndarray, traj_base: np.ndarray, cfg: SimConfig,
+                       seed: int, stream: int, d_reward: int, d_lag: int = 0, d_events: int = 0,
+                       d_params: int = 0, d_series: int = 0, series_stride: int = 0) -> None:
+        handles = np.ascontiguousarray(handles, dtype=np.uint64)
+        n_traj = np.ascontiguousarray(n_traj, dtype=np.uint32)
+        traj_base = np.ascontiguousarray(traj_base, dtype=np.uint64)
+        check(lib().ct_launch_rewards(self._h, handles.ctypes.data, n_traj.ctypes.data, traj_base.ctypes.data,
+                                      len(handles), ctypes.byref(cfg), seed, stream or None, d_params or None,
+                                      d_reward or None, d_lag or None, d_events or None, d_series or None,
+                                      series_stride))
+
+    def reduce_jobs(self, n_traj: np.ndarray, stream: int, d_reward: int, d_events: int, d_job_mean: int,
+                    d_job_events: int) -> None:
+        n_traj = np.ascontiguousarray(n_traj, dtype=np.uint32)
+        check(lib().ct_reduce_jobs(self._h, n_traj.ctypes.data, len(n_traj), stream or None, d_reward or None,
+                                   d_events or None, d_job_mean or None, d_job_events or None))
+
+    # -- host-buffer path ---------------------------------------------------------------------------
+    def rewards_host(self, handles: Sequence[int], n_traj: Sequence[int], traj_base: Sequence[int], cfg: SimConfig,
+                     seed: int, params: Optional[np.ndarray] = None, per_trajectory: bool = False):
+        handles = np.ascontiguousarray(handles, dtype=np.uint64)
+        n_traj = np.ascontiguousarray(n_traj, dtype=np.uint32)
+        traj_base = np.ascontiguousarray(traj_base, dtype=np.uint64)
+        n_jobs = len(handles)
+        total = int(n_traj.sum())
+        job_mean = np.zeros(n_jobs, dtype=np.float64)
+        job_events = np.zeros(n_jobs, dtype=np.uint64)
+        reward = np.zeros(total, dtype=np.float32) if per_trajectory else None
+        lag = np.zeros(total, dtype=np.int32) if per_trajectory else None
+        if params is not None:
+            params = np.ascontiguousarray(params, dtype=np.float32).reshape(total, N_PARAMS)
+        check(lib().ct_rewards_host(self._h, handles.ctypes.data, n_traj.ctypes.data, traj_base.ctypes.data, n_jobs,
+                                    ctypes.byref(cfg), seed, _ptr(params), job_mean.ctypes.data,
+                                    job_events.ctypes.data, _ptr(reward), _ptr(lag)))
+        out = {"job_mean": job_mean, "job_events": job_events}
+        if per_trajectory:
+            out["reward"] = reward
+            out["lag"] = lag
+        return out
+
+    def reward_from_series(self, series: np.ndarray):
+        series = np.ascontiguousarray(series, dtype=np.uint8)
+        n, nsp, n_dec = series.shape
+        reward = np.zeros(n, dtype=np.float32)
+        lag = np.zeros(n, dtype=np.int32)
+        check(lib().ct_reward_from_series_host(self._h, series.ctypes.data, n, nsp, n_dec, reward.ctypes.data,
+                                               lag.ctypes.data))
+        return reward, lag

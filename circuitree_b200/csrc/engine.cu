@@ -1,0 +1,358 @@
+// C ABI of the B200 rollout engine (include/circuitree_b200.h).  Host side only: validation, job
+// tables, stream-ordered scratch, kernel launches.  No CPU fallback: without a CUDA device every
+// compute entry point fails with CT_ERR_NO_DEVICE / CT_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/circuitree_b200.h"
+#include "ssa_pairwise.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CT_CUDA(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return fail(CT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+struct KernelInfo {
+    int blocks_per_sm = 0;
+    size_t smem = 0;
+};
+
+}  // namespace
+
+struct ct_engine {
+    int device = 0;
+    int n_sm = 0;
+    cudaStream_t stream = nullptr;   // used by the host-buffer entry points
+    KernelInfo k3, k4, k5;
+    int64_t launches = 0;
+};
+
+namespace {
+
+template <int MM>
+int prepare_kernel(KernelInfo& ki)
+{
+    ki.smem = (size_t)ct::kThreads * MM * ct::kSerStride + (ct::kThreads / 32) * ct::kSerStride * sizeof(float);
+    CT_CUDA(cudaFuncSetAttribute(ct::ssa_pairwise_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
+    CT_CUDA(cudaFuncSetAttribute(ct::ssa_pairwise_kernel<MM>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared));
+    CT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.blocks_per_sm, ct::ssa_pairwise_kernel<MM>, ct::kThreads,
+                                                          ki.smem));
+    if (ki.blocks_per_sm < 1) return fail(CT_ERR_CUDA, "SSA kernel (M=%d) does not fit on an SM", MM);
+    return CT_OK;
+}
+
+int validate_cfg(const ct_sim_config* cfg)
+{
+    if (!cfg) return fail(CT_ERR_INVALID, "cfg is NULL");
+    if (cfg->nt < 1 || cfg->decim < 1 || cfg->nt < cfg->decim) return fail(CT_ERR_INVALID, "bad nt/decim %d/%d", cfg->nt, cfg->decim);
+    if (cfg->nt / cfg->decim > CT_MAX_NDEC) return fail(CT_ERR_INVALID, "nt/decim = %d exceeds CT_MAX_NDEC", cfg->nt / cfg->decim);
+    if (!(cfg->dt > 0.0f)) return fail(CT_ERR_INVALID, "dt must be positive");
+    if (!(cfg->init_mean >= 0.0f) || cfg->init_mean > 80.0f) return fail(CT_ERR_INVALID, "init_mean out of range [0, 80]");
+    return CT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ct_last_error(void) { return g_err; }
+
+int ct_version(void) { return 100; }
+
+int ct_default_config(ct_sim_config* cfg)
+{
+    if (!cfg) return fail(CT_ERR_INVALID, "cfg is NULL");
+    static const float r[CT_N_PARAMS][3] = {
+        {-2.3f, -1.7f, 1.f}, {-1.0f, -0.4f, 1.f}, {-2.7f, -2.1f, 1.f}, {-0.3f, 0.3f, 1.f}, {0.0f, 0.6f, 1.f},
+        {-3.5f, -2.5f, 1.f}, {-1.3f, -0.7f, 1.f}, {-1.9f, -1.3f, 1.f}, {-2.0f, -1.4f, 1.f}, {-2.7f, -2.1f, 1.f}};
+    cfg->nt = 2000;
+    cfg->decim = 16;
+    cfg->dt = 20.0f;
+    cfg->init_mean = 10.0f;
+    memcpy(cfg->ranges, r, sizeof r);
+    return CT_OK;
+}
+
+int ct_engine_create(int device, ct_engine** out)
+{
+    if (!out) return fail(CT_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        (void)cudaGetLastError();
+        return fail(CT_ERR_NO_DEVICE, "no CUDA device available (%s); this engine has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n_dev) return fail(CT_ERR_INVALID, "device %d out of range [0,%d)", device, n_dev);
+    CT_CUDA(cudaSetDevice(device));
+    ct_engine* eng = new ct_engine();
+    eng->device = device;
+    cudaDeviceProp prop;
+    CT_CUDA(cudaGetDeviceProperties(&prop, device));
+    eng->n_sm = prop.multiProcessorCount;
+    CT_CUDA(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+    int rc;
+    if ((rc = prepare_kernel<3>(eng->k3)) != CT_OK) { delete eng; return rc; }
+    if ((rc = prepare_kernel<4>(eng->k4)) != CT_OK) { delete eng; return rc; }
+    if ((rc = prepare_kernel<5>(eng->k5)) != CT_OK) { delete eng; return rc; }
+    *out = eng;
+    return CT_OK;
+}
+
+int ct_engine_destroy(ct_engine* eng)
+{
+    if (!eng) return CT_OK;
+    cudaSetDevice(eng->device);
+    if (eng->stream) cudaStreamDestroy(eng->stream);
+    delete eng;
+    return CT_OK;
+}
+
+int ct_engine_info(ct_engine* eng, int32_t* n_sm, int32_t* resident_lanes)
+{
+    if (!eng) return fail(CT_ERR_INVALID, "engine is NULL");
+    if (n_sm) *n_sm = eng->n_sm;
+    if (resident_lanes) *resident_lanes = eng->n_sm * eng->k3.blocks_per_sm * ct::kThreads;
+    return CT_OK;
+}
+
+int64_t ct_engine_launch_count(ct_engine* eng) { return eng ? eng->launches : -1; }
+
+int ct_compile_topology(int32_t n_species, const int64_t* act, int32_t n_act, const int64_t* inh, int32_t n_inh,
+                        int32_t k, uint64_t* handle)
+{
+    if (!handle) return fail(CT_ERR_INVALID, "handle is NULL");
+    if (k == 3) return fail(CT_ERR_UNSUPPORTED, "dimer (k=3) topologies are not implemented yet");
+    if (k != 2) return fail(CT_ERR_INVALID, "k must be 2 or 3, got %d", k);
+    if (n_species < 1) return fail(CT_ERR_INVALID, "n_species must be >= 1");
+    if (n_species > CT_MAX_SPECIES) return fail(CT_ERR_UNSUPPORTED, "n_species %d > CT_MAX_SPECIES", n_species);
+    if (n_act < 0 || n_inh < 0 || (n_act && !act) || (n_inh && !inh)) return fail(CT_ERR_INVALID, "bad edge arrays");
+    uint64_t code = (uint64_t)n_species << 56;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int64_t* e = pass ? inh : act;
+        const int n = pass ? n_inh : n_act;
+        for (int x = 0; x < n; ++x) {
+            const int64_t i = e[2 * x], j = e[2 * x + 1];
+            if (i < 0 || j < 0 || i >= n_species || j >= n_species)
+                return fail(CT_ERR_INVALID, "edge (%lld,%lld) out of range for %d species", (long long)i, (long long)j, n_species);
+            const int sh = 2 * ((int)i * ct::kTopoStride + (int)j);
+            if ((code >> sh) & 3u) return fail(CT_ERR_INVALID, "duplicate edge (%lld,%lld)", (long long)i, (long long)j);
+            code |= (uint64_t)(pass ? 2u : 1u) << sh;
+        }
+    }
+    *handle = code;
+    return CT_OK;
+}
+
+int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n_traj, const uint64_t* traj_base,
+                      int32_t n_jobs, const ct_sim_config* cfg, uint64_t seed, void* stream_, const float* d_params,
+                      float* d_reward, int32_t* d_lag, uint32_t* d_events, uint8_t* d_series, int32_t series_stride)
+{
+    if (!eng) return fail(CT_ERR_INVALID, "engine is NULL");
+    if (n_jobs < 0 || (n_jobs && (!handles || !n_traj || !traj_base))) return fail(CT_ERR_INVALID, "bad job arrays");
+    int rc = validate_cfg(cfg);
+    if (rc != CT_OK) return rc;
+    if (n_jobs == 0) return CT_OK;
+    if (!d_reward) return fail(CT_ERR_INVALID, "d_reward is NULL");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CT_CUDA(cudaSetDevice(eng->device));
+
+    std::vector<ct::Job> jobs((size_t)n_jobs);
+    uint64_t total = 0, tiles = 0;
+    uint32_t max_nsp = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        const uint32_t nsp = ct::topo_nspecies(handles[j]);
+        if (nsp < 1 || nsp > CT_MAX_SPECIES) return fail(CT_ERR_INVALID, "job %d: bad topology handle", j);
+        if (nsp > max_nsp) max_nsp = nsp;
+        jobs[j].topo = handles[j];
+        jobs[j].traj_base = traj_base[j];
+        jobs[j].n_traj = n_traj[j];
+        jobs[j].out_offset = (uint32_t)total;
+        jobs[j].tile_start = (uint32_t)tiles;
+        jobs[j].pad = 0;
+        total += n_traj[j];
+        tiles += (n_traj[j] + ct::kTile - 1) / ct::kTile;
+        if (total > 0xffffffffull) return fail(CT_ERR_INVALID, "more than 2^32-1 trajectories in one launch");
+    }
+    if (total == 0) return CT_OK;
+    if (d_series && series_stride < (int)max_nsp * (cfg->nt / cfg->decim))
+        return fail(CT_ERR_INVALID, "series_stride %d too small", series_stride);
+
+    ct::Job* d_jobs = nullptr;
+    uint32_t* d_counter = nullptr;
+    CT_CUDA(cudaMallocAsync((void**)&d_jobs, sizeof(ct::Job) * jobs.size(), stream));
+    CT_CUDA(cudaMallocAsync((void**)&d_counter, sizeof(uint32_t), stream));
+    CT_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(ct::Job) * jobs.size(), cudaMemcpyHostToDevice, stream));
+    CT_CUDA(cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), stream));
+
+    ct::LaunchArgs A;
+    memset(&A, 0, sizeof A);
+    A.jobs = d_jobs;
+    A.n_jobs = (uint32_t)n_jobs;
+    A.n_tiles = (uint32_t)tiles;
+    A.tile_counter = d_counter;
+    A.params = d_params;
+    A.reward = d_reward;
+    A.lag = d_lag;
+    A.events = d_events;
+    A.series = d_series;
+    A.series_stride = series_stride;
+    A.log_mask = 0;
+    for (int i = 0; i < CT_N_PARAMS; ++i) {
+        A.rng_lo[i] = cfg->ranges[i][0];
+        A.rng_span[i] = cfg->ranges[i][1] - cfg->ranges[i][0];
+        if (cfg->ranges[i][2] != 0.0f) A.log_mask |= 1u << i;
+    }
+    A.seed_lo = (uint32_t)seed;
+    A.seed_hi = (uint32_t)(seed >> 32);
+    A.nt = cfg->nt;
+    A.decim = cfg->decim;
+    A.n_dec = cfg->nt / cfg->decim;
+    A.dt = cfg->dt;
+    A.init_mean = cfg->init_mean;
+
+    const KernelInfo& ki = max_nsp <= 3 ? eng->k3 : (max_nsp == 4 ? eng->k4 : eng->k5);
+    uint64_t want_blocks = (total + ct::kThreads - 1) / ct::kThreads;
+    uint64_t max_blocks = (uint64_t)eng->n_sm * ki.blocks_per_sm;
+    const unsigned grid = (unsigned)(want_blocks < max_blocks ? want_blocks : max_blocks);
+    if (max_nsp <= 3)
+        ct::ssa_pairwise_kernel<3><<<grid, ct::kThreads, ki.smem, stream>>>(A);
+    else if (max_nsp == 4)
+        ct::ssa_pairwise_kernel<4><<<grid, ct::kThreads, ki.smem, stream>>>(A);
+    else
+        ct::ssa_pairwise_kernel<5><<<grid, ct::kThreads, ki.smem, stream>>>(A);
+    CT_CUDA(cudaGetLastError());
+    eng->launches += 1;
+    CT_CUDA(cudaFreeAsync(d_jobs, stream));
+    CT_CUDA(cudaFreeAsync(d_counter, stream));
+    return CT_OK;
+}
+
+int ct_reduce_jobs(ct_engine* eng, const uint32_t* n_traj, int32_t n_jobs, void* stream_, const float* d_reward,
+                   const uint32_t* d_events, double* d_job_mean, uint64_t* d_job_events)
+{
+    if (!eng) return fail(CT_ERR_INVALID, "engine is NULL");
+    if (n_jobs < 0 || (n_jobs && (!n_traj || !d_reward || !d_job_mean))) return fail(CT_ERR_INVALID, "bad arguments");
+    if (n_jobs == 0) return CT_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CT_CUDA(cudaSetDevice(eng->device));
+    std::vector<uint32_t> off((size_t)n_jobs + 1);
+    uint64_t total = 0;
+    for (int j = 0; j < n_jobs; ++j) { off[j] = (uint32_t)total; total += n_traj[j]; }
+    off[n_jobs] = (uint32_t)total;
+    uint32_t* d_off = nullptr;
+    CT_CUDA(cudaMallocAsync((void**)&d_off, sizeof(uint32_t) * off.size(), stream));
+    CT_CUDA(cudaMemcpyAsync(d_off, off.data(), sizeof(uint32_t) * off.size(), cudaMemcpyHostToDevice, stream));
+    const int warps_per_block = 8;
+    const unsigned grid = (unsigned)((n_jobs + warps_per_block - 1) / warps_per_block);
+    ct::reduce_jobs_kernel<<<grid, warps_per_block * 32, 0, stream>>>(d_off, n_jobs, d_reward, d_events, d_job_mean,
+                                                                      (unsigned long long*)d_job_events);
+    CT_CUDA(cudaGetLastError());
+    eng->launches += 1;
+    CT_CUDA(cudaFreeAsync(d_off, stream));
+    return CT_OK;
+}
+
+int ct_rewards_host(ct_engine* eng, const uint64_t* handles, const uint32_t* n_traj, const uint64_t* traj_base,
+                    int32_t n_jobs, const ct_sim_config* cfg, uint64_t seed, const float* h_params, double* h_job_mean,
+                    uint64_t* h_job_events, float* h_reward, int32_t* h_lag)
+{
+    if (!eng) return fail(CT_ERR_INVALID, "engine is NULL");
+    if (n_jobs < 0 || (n_jobs && (!handles || !n_traj || !traj_base))) return fail(CT_ERR_INVALID, "bad job arrays");
+    if (n_jobs == 0) return CT_OK;
+    CT_CUDA(cudaSetDevice(eng->device));
+    cudaStream_t s = eng->stream;
+    uint64_t total = 0;
+    for (int j = 0; j < n_jobs; ++j) total += n_traj[j];
+    if (total == 0) {
+        for (int j = 0; j < n_jobs; ++j) { if (h_job_mean) h_job_mean[j] = 0.0; if (h_job_events) h_job_events[j] = 0; }
+        return CT_OK;
+    }
+    float *d_params = nullptr, *d_reward = nullptr;
+    int32_t* d_lag = nullptr;
+    uint32_t* d_events = nullptr;
+    double* d_mean = nullptr;
+    uint64_t* d_jev = nullptr;
+    CT_CUDA(cudaMallocAsync((void**)&d_reward, sizeof(float) * total, s));
+    CT_CUDA(cudaMallocAsync((void**)&d_lag, sizeof(int32_t) * total, s));
+    CT_CUDA(cudaMallocAsync((void**)&d_events, sizeof(uint32_t) * total, s));
+    CT_CUDA(cudaMallocAsync((void**)&d_mean, sizeof(double) * n_jobs, s));
+    CT_CUDA(cudaMallocAsync((void**)&d_jev, sizeof(uint64_t) * n_jobs, s));
+    if (h_params) {
+        CT_CUDA(cudaMallocAsync((void**)&d_params, sizeof(float) * total * CT_N_PARAMS, s));
+        CT_CUDA(cudaMemcpyAsync(d_params, h_params, sizeof(float) * total * CT_N_PARAMS, cudaMemcpyHostToDevice, s));
+    }
+    int rc = ct_launch_rewards(eng, handles, n_traj, traj_base, n_jobs, cfg, seed, s, d_params, d_reward, d_lag,
+                               d_events, nullptr, 0);
+    if (rc == CT_OK) rc = ct_reduce_jobs(eng, n_traj, n_jobs, s, d_reward, d_events, d_mean, d_jev);
+    if (rc == CT_OK) {
+        if (h_job_mean) CT_CUDA(cudaMemcpyAsync(h_job_mean, d_mean, sizeof(double) * n_jobs, cudaMemcpyDeviceToHost, s));
+        if (h_job_events) CT_CUDA(cudaMemcpyAsync(h_job_events, d_jev, sizeof(uint64_t) * n_jobs, cudaMemcpyDeviceToHost, s));
+        if (h_reward) CT_CUDA(cudaMemcpyAsync(h_reward, d_reward, sizeof(float) * total, cudaMemcpyDeviceToHost, s));
+        if (h_lag) CT_CUDA(cudaMemcpyAsync(h_lag, d_lag, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, s));
+    }
+    cudaFreeAsync(d_reward, s);
+    cudaFreeAsync(d_lag, s);
+    cudaFreeAsync(d_events, s);
+    cudaFreeAsync(d_mean, s);
+    cudaFreeAsync(d_jev, s);
+    if (d_params) cudaFreeAsync(d_params, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (rc != CT_OK) return rc;
+    if (e != cudaSuccess) return fail(CT_ERR_CUDA, "kernel execution failed: %s", cudaGetErrorString(e));
+    return CT_OK;
+}
+
+int ct_reward_from_series_host(ct_engine* eng, const uint8_t* h_series, int32_t n, int32_t n_species, int32_t n_dec,
+                               float* h_reward, int32_t* h_lag)
+{
+    if (!eng) return fail(CT_ERR_INVALID, "engine is NULL");
+    if (n < 0 || !h_series || !h_reward || !h_lag) return fail(CT_ERR_INVALID, "bad arguments");
+    if (n_species < 1 || n_species > CT_MAX_SPECIES || n_dec < 2 || n_dec > CT_MAX_NDEC)
+        return fail(CT_ERR_INVALID, "bad n_species/n_dec %d/%d", n_species, n_dec);
+    if (n == 0) return CT_OK;
+    CT_CUDA(cudaSetDevice(eng->device));
+    cudaStream_t s = eng->stream;
+    const size_t bytes = (size_t)n * n_species * n_dec;
+    uint8_t* d_series = nullptr;
+    float* d_reward = nullptr;
+    int32_t* d_lag = nullptr;
+    CT_CUDA(cudaMallocAsync((void**)&d_series, bytes, s));
+    CT_CUDA(cudaMallocAsync((void**)&d_reward, sizeof(float) * n, s));
+    CT_CUDA(cudaMallocAsync((void**)&d_lag, sizeof(int32_t) * n, s));
+    CT_CUDA(cudaMemcpyAsync(d_series, h_series, bytes, cudaMemcpyHostToDevice, s));
+    ct::reward_from_series_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_series, n, n_species, n_dec, d_reward, d_lag);
+    CT_CUDA(cudaGetLastError());
+    eng->launches += 1;
+    CT_CUDA(cudaMemcpyAsync(h_reward, d_reward, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
+    CT_CUDA(cudaMemcpyAsync(h_lag, d_lag, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+    cudaFreeAsync(d_series, s);
+    cudaFreeAsync(d_reward, s);
+    cudaFreeAsync(d_lag, s);
+    CT_CUDA(cudaStreamSynchronize(s));
+    return CT_OK;
+}
+
+}  // extern "C"
