@@ -1,2 +1,12 @@
-"""circuitree_b200 -- B200-native rollout engine behind the CircuiTree reward path."""
+"""circuitree_b200 -- B200-native rollout engine behind the CircuiTree reward path.
+
+Host-side API mirrors the reference package (``CircuiTree``, ``CircuitGrammar``,
+``SimpleNetworkGrammar``, ``DimersGrammar`` ...); the reward path itself is CUDA (sm_100a)
+reached through the C ABI in ``include/circuitree_b200.h``.
+"""
+from .circuitree import CircuiTree, ExhaustionError, ucb_score
+from .grammar import CircuitGrammar
+from .models import DimersGrammar, SimpleNetworkGrammar
+
 __version__ = "0.1.0"
+__all__ = ["CircuiTree", "CircuitGrammar", "DimersGrammar", "ExhaustionError", "SimpleNetworkGrammar", "ucb_score"]
