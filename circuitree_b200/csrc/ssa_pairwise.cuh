@@ -135,6 +135,7 @@ __device__ __forceinline__ void warp_reward(const uint8_t* ser, float* z, int ns
 template <int MM>
 struct Lane {
     float P[MM], R[MM], b[MM][MM];
+    float n[MM], A[MM];      // bound molecules at promoter j: total, and on activating edges
     float blk[MM];
     float k_on, k_off1, k_off2, km0, km1, km2, km3, kp, gm, gp;
     float t_rem;
@@ -145,48 +146,60 @@ struct Lane {
     uint32_t out;           // output slot
 };
 
+// MUFU.LG2 / MUFU.RCP without the denormal and IEEE fix-up sequences (inputs are normal here)
+__device__ __forceinline__ float fast_log2(float x)
+{
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_rcp(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ float compand_block(float s)
 {
     return fminf(floorf(sqrtf(s) + 0.5f), 255.0f);
 }
 
-// One SSA step (SPEC.md section 2).  Returns false when the trajectory has recorded its last
-// grid sample (the crossing event is not fired).
+// One SSA step (SPEC.md section 2) executed by ALL lanes of the warp in lock-step; lanes without a
+// trajectory carry zero rates (a0 = 0: nothing fires, nothing is recorded), which keeps the hot
+// loop convergent so the topology tests below are warp-uniform branches.  `topo_lo/topo_hi/nsp`
+// must be warp-uniform.  Returns false for a lane that has just recorded its last grid sample.
 template <int MM>
-__device__ __forceinline__ bool ssa_step(Lane<MM>& L, const uint64_t topo, const int nsp, uint32_t w_tau,
-                                         uint32_t w_sel, uint8_t* ser, const int nt, const int decim, const float dt)
+__device__ __forceinline__ bool ssa_step(Lane<MM>& L, const bool active, const uint32_t topo_lo,
+                                         const uint32_t topo_hi, const int nsp, uint32_t w_tau, uint32_t w_sel,
+                                         uint8_t* ser, const int nt, const int decim, const float dt)
 {
-    // ---- propensities, cumulative in SPEC order ----
-    float a[4 * MM + 2 * MM * MM];
+    auto edge = [&](int i, int j) -> uint32_t {
+        const int sh = 2 * (i * kTopoStride + j);
+        return sh < 32 ? (topo_lo >> sh) & 3u : (topo_hi >> (sh - 32)) & 3u;
+    };
+    // ---- propensities as a running sum in SPEC order; cum[r] is the sum up to reaction r ----
+    float cum[4 * MM + 2 * MM * MM];
     float c = 0.0f;
 #pragma unroll
     for (int j = 0; j < MM; ++j) {
         if (j < nsp) {
-            float n = 0.0f, na = 0.0f, ni = 0.0f;
-#pragma unroll
-            for (int i = 0; i < MM; ++i) {
-                const uint32_t e = topo_edge(topo, i, j);
-                if (e) {
-                    n += L.b[i][j];
-                    if (e == 1u) na += L.b[i][j]; else ni += L.b[i][j];
-                }
-            }
+            const float n = L.n[j], na = L.A[j];
             const float km_a = (na > 0.0f) ? L.km1 : L.km0;
             const float km_i = (na > 0.0f) ? L.km3 : L.km2;
-            a[4 * j + 0] = (ni > 0.0f) ? km_i : km_a;
-            a[4 * j + 1] = L.gm * L.R[j];
-            a[4 * j + 2] = L.kp * L.R[j];
-            a[4 * j + 3] = L.gp * L.P[j];
-            c += a[4 * j + 0]; c += a[4 * j + 1]; c += a[4 * j + 2]; c += a[4 * j + 3];
+            c += (n > na) ? km_i : km_a;     cum[4 * j + 0] = c;
+            c += L.gm * L.R[j];              cum[4 * j + 1] = c;
+            c += L.kp * L.R[j];              cum[4 * j + 2] = c;
+            c += L.gp * L.P[j];              cum[4 * j + 3] = c;
             const float koff = (n >= 2.0f) ? L.k_off2 : L.k_off1;
             const float kfree = L.k_on * (2.0f - n);
 #pragma unroll
             for (int i = 0; i < MM; ++i) {
-                if (topo_edge(topo, i, j)) {
+                if (edge(i, j)) {
+                    asm volatile("");   // keep this a (warp-uniform) branch, not predicated code
                     const int r = 4 * MM + 2 * (j * MM + i);
-                    a[r] = kfree * L.P[i];
-                    a[r + 1] = koff * L.b[i][j];
-                    c += a[r]; c += a[r + 1];
+                    c += kfree * L.P[i];     cum[r] = c;
+                    c += koff * L.b[i][j];   cum[r + 1] = c;
                 }
             }
         }
@@ -194,10 +207,9 @@ __device__ __forceinline__ bool ssa_step(Lane<MM>& L, const uint64_t topo, const
     const float a0 = c;
 
     // ---- time to next event; grid samples crossed keep the pre-event state ----
-    const float u1 = u01(w_tau);
-    const float tau = (-0.69314718056f * __log2f(u1)) * __frcp_rn(a0);   // a0 == 0 -> +inf
+    const float tau = (-0.69314718056f * fast_log2(u01(w_tau))) * fast_rcp(a0);   // a0 == 0 -> +inf
     L.t_rem -= tau;
-    if (L.t_rem < 0.0f) {
+    if (active && L.t_rem < 0.0f) {
         do {
 #pragma unroll
             for (int j = 0; j < MM; ++j) L.blk[j] += fminf(L.P[j], kSampleCap);
@@ -216,36 +228,54 @@ __device__ __forceinline__ bool ssa_step(Lane<MM>& L, const uint64_t topo, const
         if (L.k >= nt) return false;
     }
 
-    // ---- select and fire: s_r = [target < c_r] is monotone in r ----
+    // ---- select and fire: s_r = [target < cum_r] is monotone in r, so reaction r fires iff
+    //      s_r - s_{r-1} = 1; no reaction fires when a0 = 0 or rounding leaves target >= a0 ----
     const float target = u01(w_sel) * a0;
-    c = 0.0f;
     float s_prev = 0.0f;
 #pragma unroll
     for (int j = 0; j < MM; ++j) {
         if (j < nsp) {
-            c += a[4 * j + 0]; const float s_tx = (target < c) ? 1.0f : 0.0f;
-            c += a[4 * j + 1]; const float s_rm = (target < c) ? 1.0f : 0.0f;
-            c += a[4 * j + 2]; const float s_tl = (target < c) ? 1.0f : 0.0f;
-            c += a[4 * j + 3]; const float s_dp = (target < c) ? 1.0f : 0.0f;
-            L.R[j] += (s_tx - s_prev) - (s_rm - s_tx);
-            L.P[j] += (s_tl - s_rm) - (s_dp - s_tl);
+            const float s_tx = (target < cum[4 * j + 0]) ? 1.0f : 0.0f;
+            const float s_rm = (target < cum[4 * j + 1]) ? 1.0f : 0.0f;
+            const float s_tl = (target < cum[4 * j + 2]) ? 1.0f : 0.0f;
+            const float s_dp = (target < cum[4 * j + 3]) ? 1.0f : 0.0f;
+            L.R[j] += fmaf(2.0f, s_tx, -s_prev) - s_rm;
+            L.P[j] += fmaf(2.0f, s_tl, -s_rm) - s_dp;
             s_prev = s_dp;
 #pragma unroll
             for (int i = 0; i < MM; ++i) {
-                if (topo_edge(topo, i, j)) {
+                const uint32_t e = edge(i, j);
+                if (e) {
+                    asm volatile("");
                     const int r = 4 * MM + 2 * (j * MM + i);
-                    c += a[r]; const float s_b = (target < c) ? 1.0f : 0.0f;
-                    c += a[r + 1]; const float s_u = (target < c) ? 1.0f : 0.0f;
-                    const float d = (s_b - s_prev) - (s_u - s_b);   // +1 bind, -1 unbind
+                    const float s_b = (target < cum[r]) ? 1.0f : 0.0f;
+                    const float s_u = (target < cum[r + 1]) ? 1.0f : 0.0f;
+                    const float d = fmaf(2.0f, s_b, -s_prev) - s_u;   // +1 bind, -1 unbind
                     L.b[i][j] += d;
                     L.P[i] -= d;
+                    L.n[j] += d;
+                    if (e == 1u) L.A[j] += d;
                     s_prev = s_u;
                 }
             }
         }
     }
-    L.events += 1;
+    L.events += active ? 1u : 0u;
     return true;
+}
+
+// A lane without a trajectory: zero rates and state so that ssa_step is a no-op for it.
+template <int MM>
+__device__ __forceinline__ void lane_park(Lane<MM>& L)
+{
+    L.k_on = L.k_off1 = L.k_off2 = L.km0 = L.km1 = L.km2 = L.km3 = L.kp = L.gm = L.gp = 0.0f;
+#pragma unroll
+    for (int j = 0; j < MM; ++j) {
+        L.P[j] = L.R[j] = L.blk[j] = L.n[j] = L.A[j] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < MM; ++i) L.b[i][j] = 0.0f;
+    }
+    L.t_rem = 0.0f;
 }
 
 // Start trajectory `idx` of `job` on this lane (SPEC.md sections 3-5).
@@ -298,6 +328,8 @@ __device__ __forceinline__ void lane_init(Lane<MM>& L, const LaunchArgs& A, cons
     for (int j = 0; j < MM; ++j) {
         L.R[j] = 0.0f;
         L.blk[j] = 0.0f;
+        L.n[j] = 0.0f;
+        L.A[j] = 0.0f;
 #pragma unroll
         for (int i = 0; i < MM; ++i) L.b[i][j] = 0.0f;
     }
@@ -308,7 +340,7 @@ __device__ __forceinline__ void lane_init(Lane<MM>& L, const LaunchArgs& A, cons
 }
 
 template <int MM>
-__global__ void __launch_bounds__(kThreads) ssa_pairwise_kernel(const LaunchArgs A)
+__global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa_pairwise_kernel(const LaunchArgs A)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31;
@@ -318,7 +350,10 @@ __global__ void __launch_bounds__(kThreads) ssa_pairwise_kernel(const LaunchArgs
     float* z = reinterpret_cast<float*>(smem + (size_t)kThreads * (MM * kSerStride)) + warp * kSerStride;
 
     Lane<MM> L;
+    lane_park<MM>(L);
+    L.k = 0; L.kd = 0; L.dcount = 1; L.events = 0; L.ctr = 0; L.traj_lo = L.traj_hi = 0; L.out = 0;
     bool active = false, finished = false;
+    uint32_t topo_lo = 0, topo_hi = 0;   // warp-uniform copies of the topology code (see below)
     // warp-uniform tile state
     Job job;                        // job of the current tile
     job.topo = 0; job.traj_base = 0; job.n_traj = 0; job.out_offset = 0; job.tile_start = 0; job.pad = 0;
@@ -395,7 +430,13 @@ __global__ void __launch_bounds__(kThreads) ssa_pairwise_kernel(const LaunchArgs
                     const bool drained = (__ballot_sync(kFull, active) == 0u);
                     if (same || drained) {
                         job = pend; pos = pend_pos; end = pend_end;
-                        topo = job.topo; nsp = (int)topo_nspecies(topo);
+                        topo = job.topo;
+                        // Rebuild the code from one bit per lane: a vote result is warp-uniform by
+                        // construction, so the compiler can keep it in uniform registers and turn the
+                        // edge tests of ssa_step into uniform branches.
+                        topo_lo = (uint32_t)topo;
+                        topo_hi = (uint32_t)(topo >> 32);
+                        nsp = (int)((topo_hi >> 24) & 15u);
                         have_pending = false;
                         continue;
                     }
@@ -405,12 +446,25 @@ __global__ void __launch_bounds__(kThreads) ssa_pairwise_kernel(const LaunchArgs
             if (out_of_work && __ballot_sync(kFull, active) == 0u) break;
         }
 
-        if (active) {
-            Philox4 x = philox4x32_10(L.ctr, 1u, L.traj_lo, L.traj_hi, A.seed_lo, A.seed_hi);
-            L.ctr += 1;
-            bool alive = ssa_step<MM>(L, topo, nsp, x.w[0], x.w[1], ser, A.nt, A.decim, A.dt);
-            if (alive) alive = ssa_step<MM>(L, topo, nsp, x.w[2], x.w[3], ser, A.nt, A.decim, A.dt);
-            if (!alive) { active = false; finished = true; }
+        // two steps per Philox block (SPEC.md section 3); every lane runs them, parked lanes as no-ops
+        const Philox4 x = philox4x32_10(L.ctr, 1u, L.traj_lo, L.traj_hi, A.seed_lo, A.seed_hi);
+        L.ctr += 1;
+        // A warp-wide OR of identical values: the result is warp-uniform by construction, which lets
+        // the compiler keep the topology in uniform registers and branch uniformly on its bits.
+        const uint32_t u_lo = __reduce_or_sync(kFull, topo_lo);
+        const uint32_t u_hi = __reduce_or_sync(kFull, topo_hi);
+        const int u_nsp = (int)((u_hi >> 24) & 15u);
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const bool alive = ssa_step<MM>(L, active, u_lo, u_hi, u_nsp, h ? x.w[2] : x.w[0],
+                                            h ? x.w[3] : x.w[1], ser, A.nt, A.decim, A.dt);
+            if (__any_sync(kFull, !alive)) {   // rare, warp-uniform: keep the parking code off the hot path
+                if (!alive) {
+                    active = false;
+                    finished = true;
+                    lane_park<MM>(L);
+                }
+            }
         }
     }
 }
