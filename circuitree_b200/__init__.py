@@ -4,9 +4,12 @@ Host-side API mirrors the reference package (``CircuiTree``, ``CircuitGrammar``,
 ``SimpleNetworkGrammar``, ``DimersGrammar`` ...); the reward path itself is CUDA (sm_100a)
 reached through the C ABI in ``include/circuitree_b200.h``.
 """
+from . import _capi, _capi_defaults
 from .circuitree import CircuiTree, ExhaustionError, ucb_score
 from .grammar import CircuitGrammar
 from .models import DimersGrammar, SimpleNetworkGrammar
+from .oscillation import OscillationTree, RewardEngine
 
 __version__ = "0.1.0"
-__all__ = ["CircuiTree", "CircuitGrammar", "DimersGrammar", "ExhaustionError", "SimpleNetworkGrammar", "ucb_score"]
+__all__ = ["CircuiTree", "CircuitGrammar", "DimersGrammar", "ExhaustionError", "OscillationTree", "RewardEngine",
+           "SimpleNetworkGrammar", "ucb_score"]

@@ -1,0 +1,120 @@
+"""``get_reward`` on the B200: batched Gillespie SSA + in-kernel oscillation score.
+
+This is the piece the reference leaves abstract (``CircuiTree.get_reward``, reference
+circuitree/circuitree.py:135-152, called at :534 and :687).  ``OscillationTree`` is a drop-in
+``CircuiTree`` subclass: ``get_reward(state)`` turns the state into the index arrays of
+``parse_genotype`` (reference circuitree/models.py:441-480), hands them to the CUDA engine
+through the C ABI (include/circuitree_b200.h) and returns the mean reward of
+``trajectories_per_reward`` stochastic trajectories with freshly sampled parameters (SPEC.md).
+``get_rewards(states)`` does the same for a batch of leaves in ONE kernel launch.
+
+There is no CPU fallback: without the built library or without a CUDA device these calls raise.
+"""
+from __future__ import annotations
+
+import os
+from typing import Hashable, Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+from .circuitree import CircuiTree
+
+__all__ = ["OscillationTree", "RewardEngine"]
+
+
+class RewardEngine:
+    """Thin host wrapper: state strings -> topology handles -> one launch per batch."""
+
+    def __init__(self, grammar, device: Optional[int] = None, sim_config: Optional[_capi.SimConfig] = None,
+                 seed: int = 0):
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        self.grammar = grammar
+        self.device = device
+        self.cfg = sim_config if sim_config is not None else _capi.default_config()
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self._engine: Optional[_capi.Engine] = None
+        self._handles: dict[Hashable, int] = {}
+        self.next_traj = 0           # trajectory ids handed out so far (fresh Philox streams per call)
+        self.total_events = 0
+        self.total_trajectories = 0
+
+    @property
+    def engine(self) -> _capi.Engine:
+        if self._engine is None:
+            self._engine = _capi.Engine(self.device)
+        return self._engine
+
+    def handle(self, state: Hashable) -> int:
+        h = self._handles.get(state)
+        if h is None:
+            parsed = self.grammar.parse_genotype(state)
+            if len(parsed) == 3:
+                comps, act, inh = parsed
+                h = _capi.compile_topology(len(comps), act, inh, k=2)
+            else:
+                comps, regs, act, inh = parsed
+                h = _capi.compile_topology(len(comps) + len(regs), act, inh, k=3)
+            self._handles[state] = h
+        return h
+
+    def run(self, states: Sequence[Hashable], n_traj: int | Sequence[int], per_trajectory: bool = False,
+            params: Optional[np.ndarray] = None, traj_base: Optional[Sequence[int]] = None) -> dict:
+        """Simulate ``n_traj`` trajectories per state; returns per-state mean reward / event counts
+        and optionally the per-trajectory reward and lag arrays."""
+        handles = np.array([self.handle(s) for s in states], dtype=np.uint64)
+        counts = np.full(len(handles), n_traj, dtype=np.uint32) if np.isscalar(n_traj) else np.asarray(n_traj, np.uint32)
+        if traj_base is None:
+            offsets = np.concatenate(([0], np.cumsum(counts, dtype=np.uint64)[:-1])).astype(np.uint64)
+            bases = offsets + np.uint64(self.next_traj)
+            self.next_traj += int(counts.sum())
+        else:
+            bases = np.asarray(traj_base, dtype=np.uint64)
+        out = self.engine.rewards_host(handles, counts, bases, self.cfg, self.seed, params=params,
+                                       per_trajectory=per_trajectory)
+        self.total_events += int(out["job_events"].sum())
+        self.total_trajectories += int(counts.sum())
+        out["n_traj"] = counts
+        out["traj_base"] = bases
+        return out
+
+
+class OscillationTree(CircuiTree):
+    """MCTS for oscillating TF networks with the reward computed on the GPU.
+
+    Args (beyond :class:`CircuiTree`):
+        trajectories_per_reward: SSA trajectories averaged into one reward (default 32).
+        sim_config: ``_capi.SimConfig`` (time grid, parameter ranges); default = SPEC.md.
+        device: CUDA device index (default ``LOCAL_RANK`` or 0).
+        reward_seed: Philox key of the simulator (default: the tree's ``seed``).
+        success_threshold: mean reward above which :meth:`is_success` is true (default 0.4).
+    """
+
+    def __init__(self, *args, trajectories_per_reward: int = 32, sim_config=None, device: Optional[int] = None,
+                 reward_seed: Optional[int] = None, success_threshold: float = 0.4, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.trajectories_per_reward = int(trajectories_per_reward)
+        self.success_threshold = float(success_threshold)
+        self.reward_seed = int(self.seed if reward_seed is None else reward_seed) & 0xFFFFFFFFFFFFFFFF
+        self._reward_engine = RewardEngine(self.grammar, device=device, sim_config=sim_config, seed=self.reward_seed)
+        self._non_serializable_attrs.append("_reward_engine")
+
+    @property
+    def reward_engine(self) -> RewardEngine:
+        return self._reward_engine
+
+    def get_reward(self, state: Hashable, **kwargs) -> float:
+        return float(self.get_rewards([state], **kwargs)[0])
+
+    def get_rewards(self, states: Sequence[Hashable], **kwargs) -> list[float]:
+        out = self._reward_engine.run(list(states), self.trajectories_per_reward)
+        return [float(x) for x in out["job_mean"]]
+
+    def simulate(self, states: Sequence[Hashable], n_traj: int, params: Optional[np.ndarray] = None) -> dict:
+        """Per-trajectory rewards and lags for analysis (not part of the reference API)."""
+        return self._reward_engine.run(list(states), n_traj, per_trajectory=True, params=params)
+
+    def is_success(self, terminal_state: Hashable) -> bool:
+        node = self.graph.nodes[terminal_state]
+        return node["visits"] > 0 and node["reward"] / node["visits"] > self.success_threshold

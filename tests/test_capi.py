@@ -1,0 +1,75 @@
+"""The C-ABI shared library loads on a CPU-only box and exports every symbol the header declares."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from circuitree_b200 import _capi, _capi_defaults
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = ROOT / "include" / "circuitree_b200.h"
+
+
+def declared_symbols():
+    text = HEADER.read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ct_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported():
+    lib = ctypes.CDLL(str(_capi.library_path()))
+    names = declared_symbols()
+    assert len(names) >= 12
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in {HEADER.name} but not exported"
+
+
+def test_binding_covers_header():
+    lib = _capi.lib()
+    for name in declared_symbols():
+        assert getattr(lib, name).argtypes is not None or name in ("ct_version",), name
+
+
+def test_default_config_matches_spec_constants():
+    cfg = _capi.default_config()
+    d = _capi_defaults.SPEC_DEFAULTS
+    assert (cfg.nt, cfg.decim) == (d["nt"], d["decim"])
+    assert cfg.dt == d["dt"] and cfg.init_mean == d["init_mean"]
+    assert np.allclose(cfg.ranges_array(), np.array(d["ranges"]), atol=1e-6)
+    assert cfg.n_dec == 125 <= _capi.MAX_NDEC
+
+
+def test_compile_topology_validation_without_gpu():
+    h = _capi.compile_topology(3, [], [(0, 1), (1, 2), (2, 0)])
+    assert (h >> 56) & 15 == 3
+    # edge (i, j) sits at bits 2*(5*i + j): inhibition = 2
+    assert (h >> (2 * (0 * 5 + 1))) & 3 == 2 and (h >> (2 * (2 * 5 + 0))) & 3 == 2
+    assert _capi.compile_topology(2, [(0, 1)], [(1, 0)]) != _capi.compile_topology(2, [(1, 0)], [(0, 1)])
+    with pytest.raises(_capi.EngineError):
+        _capi.compile_topology(3, [(0, 3)], [])
+    with pytest.raises(_capi.EngineError):
+        _capi.compile_topology(3, [(0, 1)], [(0, 1)])          # duplicate edge
+    with pytest.raises(_capi.EngineError):
+        _capi.compile_topology(6, [], [])                       # too many species for the GPU path
+    with pytest.raises(_capi.EngineError):
+        _capi.compile_topology(3, [(0, 1, 2)], [], k=3)         # dimers: not in this round
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the engine refuses to exist instead of computing on the host."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    with pytest.raises(_capi.EngineError, match="no CUDA device|CUDA"):
+        _capi.Engine(0)
+
+
+def test_product_never_imports_oracle():
+    for path in (ROOT / "circuitree_b200").rglob("*.py"):
+        src = path.read_text()
+        assert "oracle" not in src.replace("no oracle", ""), f"{path} mentions the oracle"
+    for path in (ROOT / "circuitree_b200" / "csrc").glob("*"):
+        assert "oracle" not in path.read_text(), path

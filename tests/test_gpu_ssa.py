@@ -1,0 +1,243 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path through the C ABI vs the CPU checker.
+
+Bars (BASELINE.json north_star): reward arithmetic equal to float32 rounding on identical series;
+initial conditions identical; per-topology mean reward within 3 standard errors over 10^4
+trajectories; two-sample KS on the period (lag) distribution p > 0.01; plus size-independent
+properties (determinism, independence of launch shape and scheduling) at large batch sizes.
+The SSA model itself is this repo's SPEC.md -- upstream has none ("parity unpinned").
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from scipy import stats
+
+from circuitree_b200 import OscillationTree, RewardEngine, SimpleNetworkGrammar, _capi
+from oracle import ssa_oracle as so
+
+AI = ["activates", "inhibits"]
+THREADS = so.max_threads()
+
+
+@pytest.fixture(scope="module")
+def eng():
+    return _capi.Engine(0)
+
+
+@pytest.fixture(scope="module")
+def cfg():
+    return _capi.default_config()
+
+
+def small_cfg(nt=320, decim=16):
+    c = _capi.default_config()
+    c.nt, c.decim = nt, decim
+    return c
+
+
+def oracle_run(state, n, cfg, seed, **kw):
+    comps, act, inh = SimpleNetworkGrammar.parse_genotype(state)
+    return so.run_pairwise(len(comps), act, inh, cfg.ranges_array(), n, seed=seed, nt=cfg.nt, decim=cfg.decim,
+                           dt=cfg.dt, init_mean=cfg.init_mean, n_threads=THREADS, **kw)
+
+
+def handle_of(state):
+    comps, act, inh = SimpleNetworkGrammar.parse_genotype(state)
+    return _capi.compile_topology(len(comps), act, inh)
+
+
+def gpu_run(eng, states, n, cfg, seed, bases=None, series=False, params=None):
+    handles = [handle_of(s) for s in states]
+    counts = [n] * len(states) if np.isscalar(n) else list(n)
+    if bases is None:
+        bases = np.concatenate(([0], np.cumsum(counts)[:-1]))
+    total = int(np.sum(counts))
+    nsp = max((h >> 56) & 15 for h in handles)
+    d_reward = torch.zeros(total, device="cuda")
+    d_lag = torch.zeros(total, dtype=torch.int32, device="cuda")
+    d_events = torch.zeros(total, dtype=torch.int32, device="cuda")
+    stride = nsp * cfg.n_dec
+    d_series = torch.zeros((total, stride), dtype=torch.uint8, device="cuda") if series else None
+    d_params = torch.as_tensor(np.asarray(params, dtype=np.float32), device="cuda") if params is not None else None
+    eng.launch_rewards(handles, counts, bases, cfg, seed, 0, d_reward.data_ptr(), d_lag=d_lag.data_ptr(),
+                       d_events=d_events.data_ptr(), d_params=d_params.data_ptr() if d_params is not None else 0,
+                       d_series=d_series.data_ptr() if series else 0, series_stride=stride)
+    torch.cuda.synchronize()
+    out = {"reward": d_reward.cpu().numpy(), "lag": d_lag.cpu().numpy(), "events": d_events.cpu().numpy().astype(np.int64)}
+    if series:
+        out["series"] = d_series.cpu().numpy().reshape(total, nsp, cfg.n_dec)
+    return out
+
+
+# ---- reward stage -------------------------------------------------------------------------------------
+def test_reward_stage_matches_checker_on_random_series(eng):
+    rg = np.random.default_rng(0)
+    for nsp, n_dec in ((3, 125), (1, 125), (5, 125), (3, 20), (2, 126), (4, 3)):
+        q = rg.integers(0, 256, size=(300, nsp, n_dec), dtype=np.uint8)
+        q[0] = 7                                   # constant series: c0 = 0 -> reward 0
+        q[1, :, :] = np.arange(n_dec)[None, :]     # ramp
+        rw, lg = eng.reward_from_series(q)
+        ref = np.array([so.reward_from_series(x) for x in q])
+        assert np.abs(rw - ref[:, 0]).max() < 2e-6, (nsp, n_dec)
+        assert (lg == ref[:, 1]).mean() > 0.995, (nsp, n_dec)   # float32 vs float64 ties on near-equal minima
+        assert rw[0] == 0.0 and lg[0] == 0
+
+
+def test_reward_stage_on_simulated_series(eng, cfg):
+    o = oracle_run("*ABC::ABi_BCi_CAi", 1500, cfg, seed=11, want_series=True)
+    rw, lg = eng.reward_from_series(o["series"])
+    assert np.abs(rw - o["reward"]).max() < 2e-6
+    assert (lg == o["lag"]).mean() > 0.998
+
+
+# ---- initial conditions and sampling share the RNG streams ---------------------------------------------
+def test_first_block_and_dead_network_are_bit_identical(eng):
+    c = small_cfg(nt=64, decim=1)      # every grid sample stored: sample 0 is the Poisson initial condition
+    g = gpu_run(eng, ["*ABC::ABi_BCi_CAi"], 512, c, seed=3, series=True)
+    o = oracle_run("*ABC::ABi_BCi_CAi", 512, c, seed=3, want_series=True)
+    assert np.array_equal(g["series"][:, :, 0], o["series"][:, :, 0])
+    # zero rates: no event ever fires; the whole record is the initial state on both sides
+    z = np.zeros((64, 10), dtype=np.float32)
+    g = gpu_run(eng, ["*AB::ABa"], 64, c, seed=4, series=True, params=z)
+    o = so.run_pairwise(2, [(0, 1)], [], c.ranges_array(), 64, seed=4, nt=c.nt, decim=c.decim, dt=c.dt,
+                        init_mean=c.init_mean, explicit_params=z.astype(np.float64), want_series=True)
+    assert np.array_equal(g["series"], o["series"])
+    assert g["events"].sum() == 0 and np.all(g["reward"] == 0)
+
+
+def test_constitutive_expression_level(eng, cfg):
+    p = np.tile(np.array([0.01, 0.2, 0.004, 0.5, 0.5, 0.001, 0.001, 0.05, 0.02, 0.005], np.float32), (256, 1))
+    g = gpu_run(eng, ["*A::"], 256, cfg, seed=5, series=True, params=p)
+    level = (g["series"][:, 0, 60:].astype(float) ** 2 / 16).mean()
+    assert 235 < level < 265          # km*kp/(gm*gp) = 250
+
+
+# ---- statistical equivalence, 10^4 trajectories per topology -------------------------------------------
+TOPOLOGIES = [
+    "*ABC::ABi_BCi_CAi",                 # repressilator
+    "*AB::ABa_BAi",                      # two-component negative feedback
+    "*ABC::AAi_ABi_ACi_BAi_BBi_BCi_CAi_CBi_CCi",   # fully repressed (cheap)
+    "*ABC::ABa_BCi_CAa",
+    "*ABCD::ABi_BCi_CDi_DAi",
+    "*ABCDE::ABi_BCi_CDi_DEi_EAi",
+]
+
+
+@pytest.mark.parametrize("state", TOPOLOGIES)
+def test_statistical_equivalence(eng, cfg, state):
+    n = 10_000
+    g = gpu_run(eng, [state], n, cfg, seed=101)
+    o = oracle_run(state, n, cfg, seed=202)        # independent streams: a real two-sample test
+    se = np.sqrt(g["reward"].var(ddof=1) / n + o["reward"].var(ddof=1) / n)
+    z = (g["reward"].mean() - o["reward"].mean()) / se
+    assert abs(z) < 3.0, f"{state}: mean reward {g['reward'].mean():.4f} vs {o['reward'].mean():.4f} (z={z:.2f})"
+    ks = stats.ks_2samp(g["lag"], o["lag"])
+    assert ks.pvalue > 0.01, f"{state}: KS on lags p={ks.pvalue:.4f}"
+    se_ev = np.sqrt(g["events"].var(ddof=1) / n + o["n_events"].astype(float).var(ddof=1) / n)
+    z_ev = (g["events"].mean() - o["n_events"].mean()) / se_ev
+    assert abs(z_ev) < 3.5, f"{state}: events/trajectory {g['events'].mean():.0f} vs {o['n_events'].mean():.0f} (z={z_ev:.2f})"
+
+
+def test_same_stream_trajectories_track_the_checker(eng, cfg):
+    """With identical seeds the two sides share parameters and initial conditions; trajectories
+    decorrelate only through float32 rounding, so event counts stay strongly correlated."""
+    n = 2000
+    g = gpu_run(eng, ["*ABC::ABi_BCi_CAi"], n, cfg, seed=9)
+    o = oracle_run("*ABC::ABi_BCi_CAi", n, cfg, seed=9)
+    r = np.corrcoef(g["events"], o["n_events"].astype(float))[0, 1]
+    assert r > 0.99
+
+
+# ---- size-independent properties at scale ----------------------------------------------------------------
+def test_determinism_and_launch_shape_independence(eng, cfg):
+    state = "*ABC::ABi_BCi_CAi"
+    c = small_cfg(nt=480, decim=16)
+    n = 1 << 17
+    a = gpu_run(eng, [state], n, c, seed=77)
+    b = gpu_run(eng, [state], n, c, seed=77)
+    for k in ("reward", "lag", "events"):
+        assert np.array_equal(a[k], b[k]), k
+    # the same trajectory ids, cut into 97 ragged jobs in shuffled order
+    rg = np.random.default_rng(1)
+    cuts = np.sort(rg.choice(np.arange(1, n), size=96, replace=False))
+    starts = np.concatenate(([0], cuts)); ends = np.concatenate((cuts, [n]))
+    order = rg.permutation(97)
+    counts = (ends - starts)[order]; bases = starts[order]
+    s = gpu_run(eng, [state] * 97, counts, c, seed=77, bases=bases)
+    off = np.concatenate(([0], np.cumsum(counts)[:-1]))
+    for j in range(97):
+        sl = slice(off[j], off[j] + counts[j])
+        ref = slice(bases[j], bases[j] + counts[j])
+        assert np.array_equal(s["reward"][sl], a["reward"][ref])
+        assert np.array_equal(s["events"][sl], a["events"][ref])
+
+
+def test_mixed_topology_batch_equals_separate_launches(eng):
+    c = small_cfg(nt=320, decim=16)
+    states = ["*ABC::ABi_BCi_CAi", "*AB::ABa_BAi", "*ABC::ABa_BCi_CAa", "*A::AAi", "*ABC::", "*ABC::ABi_BCi_CAi"]
+    counts = [700, 33, 64, 1, 257, 5]
+    bases = [0, 1000, 2000, 3000, 4000, 5000]
+    mixed = gpu_run(eng, states, counts, c, seed=8, bases=bases)
+    off = np.concatenate(([0], np.cumsum(counts)))
+    for j, s in enumerate(states):
+        single = gpu_run(eng, [s], counts[j], c, seed=8, bases=[bases[j]])
+        assert np.array_equal(mixed["reward"][off[j]:off[j + 1]], single["reward"]), s
+        assert np.array_equal(mixed["events"][off[j]:off[j + 1]], single["events"]), s
+
+
+def test_empty_and_ragged_jobs(eng):
+    c = small_cfg(nt=160, decim=16)
+    out = eng.rewards_host([handle_of("*AB::ABi"), handle_of("*AB::ABa"), handle_of("*AB::ABi")], [0, 3, 0], [0, 0, 0], c, 1,
+                           per_trajectory=True)
+    assert out["job_mean"][0] == 0.0 and out["job_mean"][2] == 0.0 and len(out["reward"]) == 3
+    out = eng.rewards_host([], [], [], c, 1)
+    assert len(out["job_mean"]) == 0
+
+
+def test_host_api_matches_device_api(eng):
+    c = small_cfg(nt=320, decim=16)
+    states = ["*ABC::ABi_BCi_CAi", "*AB::ABa_BAi"]
+    dev = gpu_run(eng, states, [500, 300], c, seed=21, bases=[10, 5000])
+    host = eng.rewards_host([handle_of(s) for s in states], [500, 300], [10, 5000], c, 21, per_trajectory=True)
+    assert np.array_equal(host["reward"], dev["reward"]) and np.array_equal(host["lag"], dev["lag"])
+    assert host["job_events"].tolist() == [int(dev["events"][:500].sum()), int(dev["events"][500:].sum())]
+    assert np.allclose(host["job_mean"], [dev["reward"][:500].astype(np.float64).mean(), dev["reward"][500:].astype(np.float64).mean()], atol=1e-12)
+
+
+def test_error_codes(eng, cfg):
+    bad = _capi.default_config(); bad.nt, bad.decim = 2000, 8          # 250 stored samples > CT_MAX_NDEC
+    with pytest.raises(_capi.EngineError):
+        eng.rewards_host([handle_of("*AB::ABi")], [4], [0], bad, 1)
+    with pytest.raises(_capi.EngineError):
+        eng.rewards_host([12345], [4], [0], cfg, 1)                    # not a compiled handle (0 species)
+
+
+# ---- the reference-facing API ---------------------------------------------------------------------------
+def test_get_reward_through_circuitree_api():
+    grammar = SimpleNetworkGrammar(list("ABC"), AI, root="ABC::")
+    tree = OscillationTree(grammar=grammar, root="ABC::", seed=1, n_exhausted=np.inf, trajectories_per_reward=256)
+    r_osc = tree.get_reward("*ABC::ABi_BCi_CAi")
+    r_flat = tree.get_reward("*ABC::ABa_BCa_CAa")
+    assert 0.36 < r_osc < 0.50 and 0.12 < r_flat < 0.28 and r_osc > r_flat + 0.1
+    rs = tree.get_rewards(["*ABC::ABi_BCi_CAi", "*ABC::ABa_BCa_CAa", "*AB::ABa_BAi"])
+    assert len(rs) == 3 and abs(rs[0] - r_osc) < 0.06
+    tree.search_mcts(40)
+    assert tree.graph.nodes["ABC::"]["visits"] == 40
+    tree.search_mcts_batched(256, 64)
+    assert tree.graph.nodes["ABC::"]["visits"] == 296
+    assert 0.0 < tree.graph.nodes["ABC::"]["reward"] / 296 < 1.0
+    assert tree.reward_engine.total_trajectories == (1 + 1 + 3 + 40 + 256) * 256
+
+
+def test_same_seed_same_search():
+    def run():
+        grammar = SimpleNetworkGrammar(list("ABC"), AI, root="ABC::")
+        t = OscillationTree(grammar=grammar, root="ABC::", seed=5, n_exhausted=np.inf, trajectories_per_reward=16)
+        t.search_mcts_batched(128, 32)
+        return sorted((n, d["visits"], d["reward"]) for n, d in t.graph.nodes(data=True))
+    assert run() == run()

@@ -1,0 +1,106 @@
+"""The CPU checker itself: Philox known answers, determinism, and reward known answers.
+
+The SSA model has no upstream implementation (SPEC.md, "parity unpinned"); what can be pinned is
+the RNG (Random123 known-answer vectors) and the reward arithmetic (numpy restatement here)."""
+import numpy as np
+import pytest
+
+from oracle import ssa_oracle as so
+
+RANGES = [(-2.3, -1.7, 1), (-1.0, -0.4, 1), (-2.7, -2.1, 1), (-0.3, 0.3, 1), (0.0, 0.6, 1),
+          (-3.5, -2.5, 1), (-1.3, -0.7, 1), (-1.9, -1.3, 1), (-2.0, -1.4, 1), (-2.7, -2.1, 1)]
+REPRESSILATOR = ([], [(0, 1), (1, 2), (2, 0)])
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32-10
+    assert so.philox([0, 0, 0, 0], [0, 0]).tolist() == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert so.philox([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2).tolist() == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert so.philox([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0]).tolist() == \
+        [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+def numpy_reward(q):
+    """SPEC.md section 7 in numpy."""
+    best, best_lag = 0.0, 0
+    n = q.shape[1]
+    L = n // 2
+    for s in range(q.shape[0]):
+        y = q[s].astype(np.float64) ** 2
+        z = y - y.mean()
+        c0 = (z * z).sum()
+        if c0 <= 0:
+            continue
+        r = np.array([(z[: n - l] * z[l:]).sum() / c0 for l in range(L + 1)])
+        for l in range(1, L):
+            if r[l] < r[l - 1] and r[l] < r[l + 1] and r[l] < best:
+                best, best_lag = r[l], l
+    return min(max(-best, 0.0), 1.0), best_lag
+
+
+def test_reward_matches_numpy_restatement():
+    rg = np.random.default_rng(0)
+    for _ in range(50):
+        q = rg.integers(0, 256, size=(3, 125), dtype=np.uint8)
+        r, lag = so.reward_from_series(q)
+        r2, lag2 = numpy_reward(q)
+        assert abs(r - r2) < 1e-12 and lag == lag2
+
+
+def test_reward_known_answers():
+    k = np.arange(125)
+    sine = np.round(100 + 60 * np.sin(2 * np.pi * k / 20)).astype(np.uint8)
+    flat = np.full(125, 80, dtype=np.uint8)
+    r, lag = so.reward_from_series(np.stack([flat, sine, flat]))
+    assert lag == 10 and 0.85 < r <= 1.0          # half a period of 20 samples
+    assert so.reward_from_series(np.stack([flat, flat, flat])) == (0.0, 0)
+    ramp = np.arange(125, dtype=np.uint8)
+    assert so.reward_from_series(ramp[None, :])[0] == 0.0     # monotone ACF: no interior minimum below 0 ... or none at all
+
+
+def test_trajectories_depend_only_on_seed_and_id():
+    act, inh = REPRESSILATOR
+    a = so.run_pairwise(3, act, inh, RANGES, 24, seed=5, n_threads=1, want_series=True, want_params=True)
+    b = so.run_pairwise(3, act, inh, RANGES, 24, seed=5, n_threads=4, want_series=True, want_params=True)
+    for key in ("reward", "lag", "n_events", "series", "params"):
+        assert np.array_equal(a[key], b[key]), key
+    c = so.run_pairwise(3, act, inh, RANGES, 8, seed=5, traj_base=16, n_threads=2, want_series=True)
+    assert np.array_equal(c["series"], a["series"][16:24])
+    d = so.run_pairwise(3, act, inh, RANGES, 8, seed=6, n_threads=2)
+    assert not np.array_equal(d["n_events"], a["n_events"][:8])
+
+
+def test_sampled_parameters_respect_ranges():
+    act, inh = REPRESSILATOR
+    out = so.run_pairwise(3, act, inh, RANGES, 64, seed=1, nt=64, decim=16, n_threads=2, want_params=True)
+    logp = np.log10(out["params"])
+    for i, (lo, hi, _) in enumerate(RANGES):
+        assert logp[:, i].min() >= lo - 1e-9 and logp[:, i].max() <= hi + 1e-9
+    lin = [(v, v, 0) for v in [0.01, 0.2, 0.004, 1.0, 1.0, 0.001, 0.001, 0.05, 0.02, 0.004]]
+    out = so.run_pairwise(3, act, inh, lin, 4, seed=1, nt=64, decim=16, want_params=True)
+    assert np.allclose(out["params"], [r[0] for r in lin])
+
+
+def test_explicit_parameters_and_dead_network():
+    # all rates zero: nothing ever fires, the record repeats the initial state
+    out = so.run_pairwise(2, [], [], RANGES, 3, seed=2, nt=64, decim=16, explicit_params=np.zeros((3, 10)),
+                          want_series=True)
+    assert out["n_events"].tolist() == [0, 0, 0]
+    s = out["series"]
+    assert (s == s[:, :, :1]).all()
+    assert out["reward"].tolist() == [0.0, 0.0, 0.0]
+
+
+def test_unregulated_gene_reaches_expected_level():
+    # constitutive expression: <P> = km*kp/(gm*gp) = 0.5*0.05/(0.02*0.005) = 250
+    p = [0.01, 0.2, 0.004, 0.5, 0.5, 0.001, 0.001, 0.05, 0.02, 0.005]
+    out = so.run_pairwise(1, [], [], RANGES, 64, seed=3, explicit_params=np.tile(p, (64, 1)), n_threads=4, want_series=True)
+    mean_late = (out["series"][:, 0, 60:].astype(float) ** 2 / 16).mean()
+    assert 230 < mean_late < 270
+
+
+def test_invalid_inputs():
+    with pytest.raises(ValueError):
+        so.run_pairwise(3, [(0, 5)], [], RANGES, 1)
+    with pytest.raises(ValueError):
+        so.run_pairwise(9, [], [], RANGES, 1)
