@@ -1,0 +1,688 @@
+// Native host side of the batched MCTS scheduler: bit-packed SimpleNetworkGrammar states,
+// canonicalisation over component permutations, action generation, UCB selection, random
+// rollouts, visit/reward back-propagation and exhaustion bookkeeping.
+//
+// It restates, on packed 64-bit states, exactly what the reference does on strings:
+//   get_actions / do_action            reference circuitree/models.py:164-270
+//   get_unique_state (min relabelling) reference circuitree/models.py:337-400
+//   select_and_expand, ucb_score       reference circuitree/circuitree.py:21-57, :315-384
+//   random rollout                     reference circuitree/circuitree.py:218-246
+//   _backpropagate                     reference circuitree/circuitree.py:451-466
+//   mark_as_exhausted                  reference circuitree/circuitree.py:386-420
+//   grow_tree                          reference circuitree/circuitree.py:539-586
+// including the consumption of numpy's PCG64 stream by Generator.shuffle / Generator.choice, so
+// that for identical rewards the tree is identical to the reference's, node for node.
+//
+// Scope: all components present in the root (e.g. "ABC::"), at most 5 components and 3
+// interaction types, no fixed components.  Anything else stays on the Python path.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/circuitree_b200.h"
+
+namespace {
+
+thread_local char t_err[512] = "";
+int tfail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof t_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+typedef unsigned __int128 u128;
+
+// ---- numpy's PCG64 (XSL-RR 128/64) and the two bounded-integer algorithms the reference uses ----
+struct Pcg64 {
+    u128 state = 0, inc = 0;
+    int has_uint32 = 0;
+    uint32_t uinteger = 0;
+
+    uint64_t next64()
+    {
+        const u128 mult = ((u128)0x2360ED051FC65DA4ull << 64) | 0x4385DF649FCCF645ull;
+        state = state * mult + inc;
+        const uint64_t hi = (uint64_t)(state >> 64), lo = (uint64_t)state;
+        const unsigned rot = (unsigned)(state >> 122);
+        const uint64_t x = hi ^ lo;
+        return (x >> rot) | (x << ((-rot) & 63));
+    }
+    uint32_t next32()
+    {
+        if (has_uint32) { has_uint32 = 0; return uinteger; }
+        const uint64_t n = next64();
+        has_uint32 = 1;
+        uinteger = (uint32_t)(n >> 32);
+        return (uint32_t)n;
+    }
+    // numpy random_interval(max): masked rejection, used by Generator.shuffle on a list
+    uint64_t interval(uint64_t max)
+    {
+        if (max == 0) return 0;
+        uint64_t mask = max, value;
+        mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16; mask |= mask >> 32;
+        if (max <= 0xffffffffull) { while ((value = (next32() & mask)) > max) {} }
+        else { while ((value = (next64() & mask)) > max) {} }
+        return value;
+    }
+    // numpy Generator.integers(0, n) for n <= 2^32 (Lemire, 32-bit buffered), used by Generator.choice
+    uint64_t below(uint64_t n)
+    {
+        const uint64_t rng = n - 1;
+        if (rng == 0) return 0;
+        if (rng == 0xffffffffull) return next32();
+        const uint32_t rng_excl = (uint32_t)rng + 1u;
+        uint64_t m = (uint64_t)next32() * rng_excl;
+        uint32_t leftover = (uint32_t)m;
+        if (leftover < rng_excl) {
+            const uint32_t threshold = (0xffffffffu - (uint32_t)rng) % rng_excl;
+            while (leftover < threshold) {
+                m = (uint64_t)next32() * rng_excl;
+                leftover = (uint32_t)m;
+            }
+        }
+        return m >> 32;
+    }
+    template <typename T>
+    void shuffle(std::vector<T>& x)
+    {
+        for (size_t i = x.size(); i-- > 1;) {
+            const size_t j = (size_t)interval(i);
+            std::swap(x[i], x[j]);
+        }
+    }
+};
+
+constexpr uint64_t kTerminalBit = 1ull << 62;
+constexpr int kMaxN = 5;
+
+struct Node {
+    uint64_t key;
+    int64_t visits = 0;
+    double reward = 0.0;
+    bool exhausted = false;
+    std::vector<int> out_edges, in_edges;   // insertion order, like networkx adjacency dicts
+    int64_t sync_visits = 0;                // values at the last delta collection (multi-GPU merge)
+    double sync_reward = 0.0;
+};
+struct Edge {
+    int parent, child;
+    int64_t visits = 0;
+    double reward = 0.0;
+    int64_t sync_visits = 0;
+    double sync_reward = 0.0;
+};
+
+}  // namespace
+
+struct ct_tree {
+    int n = 0, n_types = 0, n_cells = 0, max_interactions = 0;
+    char comp_letter[kMaxN];       // sorted index -> letter
+    int decl_comp[kMaxN];          // declaration index -> sorted index
+    char type_letter[3];           // type code (rank by letter) -> letter
+    int decl_type[3];              // declaration index -> type code
+    std::vector<std::vector<uint8_t>> perm_cell;   // perm -> cell -> cell
+    uint64_t all_absent = 0;
+    double c_ucb = std::sqrt(2.0);
+    bool track_exhaustion = false;
+    double n_exhausted = 0.0;
+    Pcg64 rng;
+    std::vector<double> log_table;
+    uint64_t root_key = 0;
+    std::vector<Node> nodes;
+    std::vector<Edge> edges;
+    std::unordered_map<uint64_t, int> index;
+    std::unordered_map<uint64_t, uint64_t> canon_memo;
+    std::vector<std::vector<int>> pending;   // paths (node ids) awaiting rewards, FIFO
+    size_t pending_head = 0;
+    bool exhausted_all = false;
+
+    int shift(int cell) const { return 2 * (n_cells - 1 - cell); }
+    uint32_t cell(uint64_t key, int c) const { return (uint32_t)(key >> shift(c)) & 3u; }
+
+    uint64_t canonical(uint64_t key)
+    {
+        const uint64_t flags = key & kTerminalBit;
+        const uint64_t body = key & ~kTerminalBit;
+        auto it = canon_memo.find(body);
+        if (it != canon_memo.end()) return it->second | flags;
+        int cells[kMaxN * kMaxN], codes[kMaxN * kMaxN], ne = 0;
+        for (int c = 0; c < n_cells; ++c) {
+            const uint32_t v = cell(body, c);
+            if (v != 3u) { cells[ne] = c; codes[ne] = (int)v; ++ne; }
+        }
+        uint64_t best = ~0ull;
+        for (const auto& pm : perm_cell) {
+            uint64_t k = all_absent;
+            for (int e = 0; e < ne; ++e) k ^= (uint64_t)(3u ^ (uint32_t)codes[e]) << shift(pm[cells[e]]);
+            if (k < best) best = k;
+        }
+        if (canon_memo.size() > (1u << 22)) canon_memo.clear();
+        canon_memo.emplace(body, best);
+        return best | flags;
+    }
+
+    // action ids: 0 = *terminate*, 1 + (decl_pair * n_types + decl_type) = add interaction
+    void actions(uint64_t key, std::vector<int>& out) const
+    {
+        out.clear();
+        if (key & kTerminalBit) return;
+        int n_ixn = 0;
+        bool touched[kMaxN] = {false, false, false, false, false};
+        for (int c = 0; c < n_cells; ++c)
+            if (cell(key, c) != 3u) { ++n_ixn; touched[c / n] = true; touched[c % n] = true; }
+        if (n_ixn >= max_interactions) { out.push_back(0); return; }
+        if (n_ixn > 0) out.push_back(0);
+        for (int di = 0; di < n; ++di)
+            for (int dj = 0; dj < n; ++dj) {
+                const int si = decl_comp[di], sj = decl_comp[dj];
+                if (n_ixn > 0) {
+                    if (cell(key, si * n + sj) != 3u) continue;
+                    if (!touched[si] && !touched[sj]) continue;
+                }
+                for (int t = 0; t < n_types; ++t) out.push_back(1 + (di * n + dj) * n_types + t);
+            }
+    }
+    uint64_t apply(uint64_t key, int action) const
+    {
+        if (action == 0) return key | kTerminalBit;
+        const int a = action - 1, t = a % n_types, pair = a / n_types;
+        const int si = decl_comp[pair / n], sj = decl_comp[pair % n];
+        const int sh = shift(si * n + sj);
+        return (key & ~(3ull << sh)) | ((uint64_t)decl_type[t] << sh);
+    }
+    uint64_t step(uint64_t key, int action) { return canonical(apply(key, action)); }
+
+    int node_of(uint64_t key) const
+    {
+        auto it = index.find(key);
+        return it == index.end() ? -1 : it->second;
+    }
+    int add_node(uint64_t key)
+    {
+        const int id = (int)nodes.size();
+        nodes.emplace_back();
+        nodes.back().key = key;
+        index.emplace(key, id);
+        return id;
+    }
+    int edge_of(int parent, int child) const
+    {
+        for (int e : nodes[parent].out_edges)
+            if (edges[e].child == child) return e;
+        return -1;
+    }
+    int add_edge(int parent, int child)
+    {
+        const int id = (int)edges.size();
+        edges.emplace_back();
+        edges.back().parent = parent;
+        edges.back().child = child;
+        nodes[parent].out_edges.push_back(id);
+        nodes[child].in_edges.push_back(id);
+        return id;
+    }
+    double log_of(int64_t v) const
+    {
+        if (v >= 0 && (size_t)v < log_table.size()) return log_table[(size_t)v];
+        return std::log((double)v);
+    }
+
+    // returns false when the whole tree is exhausted (the reference raises ExhaustionError)
+    bool mark_exhausted(int node)
+    {
+        nodes[node].exhausted = true;
+        if (nodes[node].key == root_key) { exhausted_all = true; return false; }
+        for (int e : nodes[node].in_edges) {
+            Node& p = nodes[edges[e].parent];
+            p.visits -= edges[e].visits;
+            p.reward -= edges[e].reward;
+        }
+        for (size_t x = 0; x < nodes[node].in_edges.size(); ++x) {
+            const int parent = edges[nodes[node].in_edges[x]].parent;
+            bool all = true;
+            for (int e : nodes[parent].out_edges)
+                if (!nodes[edges[e].child].exhausted) { all = false; break; }
+            if (all && !mark_exhausted(parent)) return false;
+        }
+        return true;
+    }
+
+    // 0 ok, 1 tree exhausted, 2 dead end (every child exhausted or NaN scores: the reference crashes here)
+    int select_and_expand(std::vector<int>& path)
+    {
+        std::vector<int> acts;
+        int node = node_of(root_key);
+        path.assign(1, node);
+        actions(nodes[node].key, acts);
+        const double inf = std::numeric_limits<double>::infinity();
+        while (!acts.empty()) {
+            rng.shuffle(acts);
+            int best = -1;
+            double best_score = -inf;
+            for (int a : acts) {
+                const uint64_t ck = step(nodes[node].key, a);
+                int child = node_of(ck);
+                if (track_exhaustion && child >= 0 && nodes[child].exhausted) continue;
+                const int e = child >= 0 ? edge_of(node, child) : -1;
+                double score = inf;
+                if (e >= 0 && edges[e].visits != 0)
+                    score = edges[e].reward / (double)edges[e].visits +
+                            c_ucb * std::sqrt(log_of(nodes[node].visits) / (double)edges[e].visits);
+                if (score == inf) {
+                    if (child < 0) child = add_node(ck);
+                    if (e < 0) add_edge(node, child);
+                    path.push_back(child);
+                    return 0;
+                }
+                if (score > best_score) { best = child; best_score = score; }
+            }
+            if (best < 0) return 2;
+            node = best;
+            path.push_back(node);
+            actions(nodes[node].key, acts);
+        }
+        if (track_exhaustion && (double)nodes[node].visits >= n_exhausted - 1.0)
+            if (!mark_exhausted(node)) return 1;
+        return 0;
+    }
+
+    uint64_t rollout(uint64_t key)
+    {
+        std::vector<int> acts;
+        while (!(key & kTerminalBit)) {
+            actions(key, acts);
+            key = step(key, acts[(size_t)rng.below(acts.size())]);
+        }
+        return key;
+    }
+
+    template <typename F>
+    void along(const std::vector<int>& path, F f)
+    {
+        int child = path.back();
+        f(nodes[child].visits, nodes[child].reward);
+        for (size_t x = path.size() - 1; x-- > 0;) {
+            const int parent = path[x];
+            Edge& e = edges[edge_of(parent, child)];
+            f(e.visits, e.reward);
+            f(nodes[parent].visits, nodes[parent].reward);
+            child = parent;
+        }
+    }
+
+    std::string to_string(uint64_t key) const
+    {
+        std::string s;
+        if (key & kTerminalBit) s += '*';
+        for (int i = 0; i < n; ++i) s += comp_letter[i];
+        s += "::";
+        bool first = true;
+        for (int c = 0; c < n_cells; ++c) {
+            const uint32_t v = cell(key, c);
+            if (v == 3u) continue;
+            if (!first) s += '_';
+            first = false;
+            s += comp_letter[c / n];
+            s += comp_letter[c % n];
+            s += type_letter[v];
+        }
+        return s;
+    }
+    bool from_string(const char* str, uint64_t* out)
+    {
+        const char* p = str;
+        uint64_t key = all_absent;
+        if (*p == '*') { key |= kTerminalBit; ++p; }
+        const char* sep = strstr(p, "::");
+        if (!sep) return false;
+        // every component must be present (any order)
+        if ((int)(sep - p) != n) return false;
+        for (int i = 0; i < n; ++i)
+            if (!memchr(p, comp_letter[i], (size_t)n)) return false;
+        p = sep + 2;
+        while (*p) {
+            if (strlen(p) < 3) return false;
+            int si = -1, sj = -1, tc = -1;
+            for (int i = 0; i < n; ++i) { if (comp_letter[i] == p[0]) si = i; if (comp_letter[i] == p[1]) sj = i; }
+            for (int t = 0; t < n_types; ++t) if (type_letter[t] == p[2]) tc = t;
+            if (si < 0 || sj < 0 || tc < 0) return false;
+            const int sh = shift(si * n + sj);
+            key = (key & ~(3ull << sh)) | ((uint64_t)tc << sh);
+            p += 3;
+            if (*p == '_') ++p; else if (*p) return false;
+        }
+        *out = key;
+        return true;
+    }
+    // GPU topology handle (ct_compile_topology layout): type letter 'a' -> 1, 'i' -> 2
+    bool to_handle(uint64_t key, uint64_t* handle) const
+    {
+        uint64_t h = (uint64_t)n << 56;
+        for (int c = 0; c < n_cells; ++c) {
+            const uint32_t v = cell(key, c);
+            if (v == 3u) continue;
+            const char t = type_letter[v];
+            const uint64_t code = t == 'a' ? 1u : (t == 'i' ? 2u : 0u);
+            if (!code) return false;
+            h |= code << (2 * ((c / n) * 5 + (c % n)));
+        }
+        *handle = h;
+        return true;
+    }
+};
+
+extern "C" {
+
+const char* ct_tree_last_error(void) { return t_err; }
+
+int ct_tree_create(const char* components, const char* types, int32_t max_interactions, const char* root,
+                   double exploration_constant, double n_exhausted, ct_tree** out)
+{
+    if (!components || !types || !root || !out) return tfail(CT_ERR_INVALID, "NULL argument");
+    const int n = (int)strlen(components), nt = (int)strlen(types);
+    if (n < 1 || n > kMaxN) return tfail(CT_ERR_UNSUPPORTED, "native tree supports 1..5 components, got %d", n);
+    if (nt < 1 || nt > 3) return tfail(CT_ERR_UNSUPPORTED, "native tree supports 1..3 interaction types, got %d", nt);
+    ct_tree* t = new ct_tree();
+    t->n = n; t->n_types = nt; t->n_cells = n * n;
+    t->max_interactions = max_interactions < 0 ? n * n : max_interactions;
+    std::string sc(components), st(types);
+    std::sort(sc.begin(), sc.end());
+    std::sort(st.begin(), st.end());
+    if (std::adjacent_find(sc.begin(), sc.end()) != sc.end() || std::adjacent_find(st.begin(), st.end()) != st.end()) {
+        delete t;
+        return tfail(CT_ERR_INVALID, "component / interaction codes must be unique");
+    }
+    for (int i = 0; i < n; ++i) { t->comp_letter[i] = sc[i]; t->decl_comp[i] = (int)sc.find(components[i]); }
+    for (int i = 0; i < nt; ++i) { t->type_letter[i] = st[i]; t->decl_type[i] = (int)st.find(types[i]); }
+    t->all_absent = 0;
+    for (int c = 0; c < t->n_cells; ++c) t->all_absent |= 3ull << t->shift(c);
+    std::vector<int> p(n);
+    for (int i = 0; i < n; ++i) p[i] = i;
+    do {
+        std::vector<uint8_t> m((size_t)t->n_cells);
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) m[i * n + j] = (uint8_t)(p[i] * n + p[j]);
+        t->perm_cell.push_back(m);
+    } while (std::next_permutation(p.begin(), p.end()));
+    t->c_ucb = exploration_constant;
+    t->track_exhaustion = !std::isnan(n_exhausted);
+    t->n_exhausted = n_exhausted;
+    uint64_t rk;
+    if (!t->from_string(root, &rk)) {
+        delete t;
+        return tfail(CT_ERR_UNSUPPORTED, "root '%s' must contain every component exactly once", root);
+    }
+    if (t->to_string(rk) != root) {
+        delete t;
+        return tfail(CT_ERR_UNSUPPORTED, "root '%s' is not in sorted form (expected '%s')", root, t->to_string(rk).c_str());
+    }
+    t->root_key = rk;
+    t->add_node(rk);
+    *out = t;
+    return CT_OK;
+}
+
+int ct_tree_destroy(ct_tree* t) { delete t; return CT_OK; }
+
+int ct_tree_set_rng(ct_tree* t, const uint64_t state[2], const uint64_t inc[2], int32_t has_uint32, uint32_t uinteger)
+{
+    if (!t || !state || !inc) return tfail(CT_ERR_INVALID, "NULL argument");
+    t->rng.state = ((u128)state[1] << 64) | state[0];
+    t->rng.inc = ((u128)inc[1] << 64) | inc[0];
+    t->rng.has_uint32 = has_uint32;
+    t->rng.uinteger = uinteger;
+    return CT_OK;
+}
+
+int ct_tree_get_rng(ct_tree* t, uint64_t state[2], uint64_t inc[2], int32_t* has_uint32, uint32_t* uinteger)
+{
+    if (!t || !state || !inc || !has_uint32 || !uinteger) return tfail(CT_ERR_INVALID, "NULL argument");
+    state[0] = (uint64_t)t->rng.state; state[1] = (uint64_t)(t->rng.state >> 64);
+    inc[0] = (uint64_t)t->rng.inc; inc[1] = (uint64_t)(t->rng.inc >> 64);
+    *has_uint32 = t->rng.has_uint32;
+    *uinteger = t->rng.uinteger;
+    return CT_OK;
+}
+
+int ct_tree_set_log_table(ct_tree* t, const double* table, int64_t n)
+{
+    if (!t || (n && !table) || n < 0) return tfail(CT_ERR_INVALID, "bad log table");
+    t->log_table.assign(table, table + n);
+    return CT_OK;
+}
+
+/* Test hook: draw from the RNG like Generator.shuffle (kind 0: returns the permutation of 0..n-1)
+ * or Generator.integers(0, n) (kind 1: out[0]). */
+int ct_tree_rng_draw(ct_tree* t, int32_t kind, int64_t n, int64_t* out)
+{
+    if (!t || !out || n < 1) return tfail(CT_ERR_INVALID, "bad arguments");
+    if (kind == 0) {
+        std::vector<int64_t> v((size_t)n);
+        for (int64_t i = 0; i < n; ++i) v[(size_t)i] = i;
+        t->rng.shuffle(v);
+        memcpy(out, v.data(), sizeof(int64_t) * (size_t)n);
+    } else {
+        out[0] = (int64_t)t->rng.below((uint64_t)n);
+    }
+    return CT_OK;
+}
+
+/* Select k leaves under virtual loss: select_and_expand, random rollout, visit back-propagation
+ * (the order of reference circuitree.py:529-533).  sim_keys / sim_handles (nullable) receive the
+ * packed terminal state and the GPU topology handle of each simulated state.  Returns the number
+ * selected in *n_done (fewer than k only when the tree is exhausted). */
+int ct_tree_select(ct_tree* t, int32_t k, uint64_t* sim_keys, uint64_t* sim_handles, int32_t* n_done)
+{
+    if (!t || k < 0 || !n_done) return tfail(CT_ERR_INVALID, "bad arguments");
+    *n_done = 0;
+    std::vector<int> path;
+    for (int x = 0; x < k; ++x) {
+        const int rc = t->select_and_expand(path);
+        if (rc == 1) return tfail(100, "ExhaustionError: every node in the tree has been visited to exhaustion");
+        if (rc == 2) return tfail(CT_ERR_INVALID, "selection reached a node without selectable children");
+        const uint64_t sim = t->rollout(t->nodes[path.back()].key);
+        t->along(path, [](int64_t& v, double&) { v += 1; });
+        if (sim_keys) sim_keys[x] = sim;
+        if (sim_handles && !t->to_handle(sim, &sim_handles[x]))
+            return tfail(CT_ERR_UNSUPPORTED, "state has interaction types other than a/i");
+        t->pending.push_back(path);
+        *n_done = x + 1;
+    }
+    return CT_OK;
+}
+
+/* Back-propagate rewards for the k oldest pending selections (FIFO). */
+int ct_tree_backprop(ct_tree* t, int32_t k, const double* rewards)
+{
+    if (!t || k < 0 || (k && !rewards)) return tfail(CT_ERR_INVALID, "bad arguments");
+    if ((size_t)k > t->pending.size() - t->pending_head) return tfail(CT_ERR_INVALID, "more rewards than pending selections");
+    for (int x = 0; x < k; ++x) {
+        const double r = rewards[x];
+        t->along(t->pending[t->pending_head + x], [r](int64_t&, double& w) { w += r; });
+    }
+    t->pending_head += (size_t)k;
+    if (t->pending_head == t->pending.size()) { t->pending.clear(); t->pending_head = 0; }
+    return CT_OK;
+}
+
+/* Paths of the pending selections: lengths[k] and node ids concatenated (nullable ids to size). */
+int ct_tree_pending(ct_tree* t, int32_t* n_pending, int32_t* lengths, int32_t* ids)
+{
+    if (!t || !n_pending) return tfail(CT_ERR_INVALID, "bad arguments");
+    const size_t np = t->pending.size() - t->pending_head;
+    *n_pending = (int32_t)np;
+    size_t off = 0;
+    for (size_t x = 0; x < np; ++x) {
+        const auto& p = t->pending[t->pending_head + x];
+        if (lengths) lengths[x] = (int32_t)p.size();
+        if (ids) for (size_t y = 0; y < p.size(); ++y) ids[off + y] = p[y];
+        off += p.size();
+    }
+    return CT_OK;
+}
+
+int ct_tree_size(ct_tree* t, int64_t* n_nodes, int64_t* n_edges)
+{
+    if (!t) return tfail(CT_ERR_INVALID, "NULL tree");
+    if (n_nodes) *n_nodes = (int64_t)t->nodes.size();
+    if (n_edges) *n_edges = (int64_t)t->edges.size();
+    return CT_OK;
+}
+
+int ct_tree_export(ct_tree* t, uint64_t* node_keys, int64_t* node_visits, double* node_reward, uint8_t* node_exhausted,
+                   int32_t* edge_parent, int32_t* edge_child, int64_t* edge_visits, double* edge_reward)
+{
+    if (!t) return tfail(CT_ERR_INVALID, "NULL tree");
+    for (size_t i = 0; i < t->nodes.size(); ++i) {
+        if (node_keys) node_keys[i] = t->nodes[i].key;
+        if (node_visits) node_visits[i] = t->nodes[i].visits;
+        if (node_reward) node_reward[i] = t->nodes[i].reward;
+        if (node_exhausted) node_exhausted[i] = t->nodes[i].exhausted;
+    }
+    for (size_t i = 0; i < t->edges.size(); ++i) {
+        if (edge_parent) edge_parent[i] = t->edges[i].parent;
+        if (edge_child) edge_child[i] = t->edges[i].child;
+        if (edge_visits) edge_visits[i] = t->edges[i].visits;
+        if (edge_reward) edge_reward[i] = t->edges[i].reward;
+    }
+    return CT_OK;
+}
+
+int ct_tree_key_to_string(ct_tree* t, uint64_t key, char* buf, int32_t buflen)
+{
+    if (!t || !buf) return tfail(CT_ERR_INVALID, "NULL argument");
+    const std::string s = t->to_string(key);
+    if ((int)s.size() + 1 > buflen) return tfail(CT_ERR_INVALID, "buffer too small");
+    memcpy(buf, s.c_str(), s.size() + 1);
+    return CT_OK;
+}
+
+/* Parse a state string; canonical != 0 also applies get_unique_state. */
+int ct_tree_string_to_key(ct_tree* t, const char* s, int32_t canonical, uint64_t* key)
+{
+    if (!t || !s || !key) return tfail(CT_ERR_INVALID, "NULL argument");
+    uint64_t k;
+    if (!t->from_string(s, &k)) return tfail(CT_ERR_INVALID, "cannot parse state '%s'", s);
+    *key = canonical ? t->canonical(k) : k;
+    return CT_OK;
+}
+
+/* Action ids of a packed state in the reference's order; returns the count (ids nullable). */
+int ct_tree_actions(ct_tree* t, uint64_t key, int32_t* ids, int32_t cap, int32_t* n_out)
+{
+    if (!t || !n_out) return tfail(CT_ERR_INVALID, "NULL argument");
+    std::vector<int> a;
+    t->actions(key, a);
+    *n_out = (int32_t)a.size();
+    if (ids) for (size_t i = 0; i < a.size() && (int32_t)i < cap; ++i) ids[i] = a[i];
+    return CT_OK;
+}
+
+int ct_tree_do_action(ct_tree* t, uint64_t key, int32_t action, uint64_t* out)
+{
+    if (!t || !out) return tfail(CT_ERR_INVALID, "NULL argument");
+    *out = t->step(key, action);
+    return CT_OK;
+}
+
+int ct_tree_key_to_handle(ct_tree* t, uint64_t key, uint64_t* handle)
+{
+    if (!t || !handle) return tfail(CT_ERR_INVALID, "NULL argument");
+    if (!t->to_handle(key, handle)) return tfail(CT_ERR_UNSUPPORTED, "state has interaction types other than a/i");
+    return CT_OK;
+}
+
+/* Exhaustive expansion from the root in the reference's stack order (circuitree.py:565-586). */
+int ct_tree_grow(ct_tree* t)
+{
+    if (!t) return tfail(CT_ERR_INVALID, "NULL tree");
+    std::vector<std::pair<int, int>> stack;
+    std::vector<int> acts;
+    const int root = t->node_of(t->root_key);
+    t->actions(t->root_key, acts);
+    for (int a : acts) stack.emplace_back(root, a);
+    while (!stack.empty()) {
+        const auto [node, action] = stack.back();
+        stack.pop_back();
+        if (t->nodes[node].key & kTerminalBit) continue;
+        const uint64_t ck = t->step(t->nodes[node].key, action);
+        int child = t->node_of(ck);
+        if (child < 0) {
+            child = t->add_node(ck);
+            t->actions(ck, acts);
+            for (int a : acts) stack.emplace_back(child, a);
+        }
+        if (t->edge_of(node, child) < 0) t->add_edge(node, child);
+    }
+    return CT_OK;
+}
+
+/* Multi-GPU root-parallel merge, step 1: changes of (visits, reward) since the previous call, as
+ * sparse records keyed by packed state.  Call with NULL arrays to get the counts. */
+int ct_tree_collect_deltas(ct_tree* t, int64_t* n_node_recs, uint64_t* node_key, int64_t* node_dv, double* node_dr,
+                           int64_t* n_edge_recs, uint64_t* edge_pkey, uint64_t* edge_ckey, int64_t* edge_dv, double* edge_dr)
+{
+    if (!t || !n_node_recs || !n_edge_recs) return tfail(CT_ERR_INVALID, "NULL argument");
+    const bool fill = node_key != nullptr;
+    int64_t nn = 0, ne = 0;
+    for (auto& nd : t->nodes) {
+        if (nd.visits == nd.sync_visits && nd.reward == nd.sync_reward) continue;
+        if (fill) {
+            node_key[nn] = nd.key; node_dv[nn] = nd.visits - nd.sync_visits; node_dr[nn] = nd.reward - nd.sync_reward;
+            nd.sync_visits = nd.visits; nd.sync_reward = nd.reward;
+        }
+        ++nn;
+    }
+    for (auto& e : t->edges) {
+        if (e.visits == e.sync_visits && e.reward == e.sync_reward) continue;   // incl. expanded-but-unvisited edges
+        if (fill) {
+            edge_pkey[ne] = t->nodes[e.parent].key; edge_ckey[ne] = t->nodes[e.child].key;
+            edge_dv[ne] = e.visits - e.sync_visits; edge_dr[ne] = e.reward - e.sync_reward;
+            e.sync_visits = e.visits; e.sync_reward = e.reward;
+        }
+        ++ne;
+    }
+    *n_node_recs = nn;
+    *n_edge_recs = ne;
+    return CT_OK;
+}
+
+/* Step 2: add other ranks' records (nodes and edges are created as needed).  Merged statistics are
+ * the sums of all ranks' increments -- what one tree would hold had it executed every path. */
+int ct_tree_merge_deltas(ct_tree* t, int64_t n_node_recs, const uint64_t* node_key, const int64_t* node_dv, const double* node_dr,
+                         int64_t n_edge_recs, const uint64_t* edge_pkey, const uint64_t* edge_ckey, const int64_t* edge_dv,
+                         const double* edge_dr)
+{
+    if (!t) return tfail(CT_ERR_INVALID, "NULL tree");
+    for (int64_t x = 0; x < n_node_recs; ++x) {
+        int id = t->node_of(node_key[x]);
+        if (id < 0) id = t->add_node(node_key[x]);
+        Node& nd = t->nodes[id];
+        nd.visits += node_dv[x]; nd.reward += node_dr[x];
+        nd.sync_visits += node_dv[x]; nd.sync_reward += node_dr[x];
+    }
+    for (int64_t x = 0; x < n_edge_recs; ++x) {
+        int p = t->node_of(edge_pkey[x]), c = t->node_of(edge_ckey[x]);
+        if (p < 0) p = t->add_node(edge_pkey[x]);
+        if (c < 0) c = t->add_node(edge_ckey[x]);
+        int e = t->edge_of(p, c);
+        if (e < 0) e = t->add_edge(p, c);
+        Edge& ed = t->edges[e];
+        ed.visits += edge_dv[x]; ed.reward += edge_dr[x];
+        ed.sync_visits += edge_dv[x]; ed.sync_reward += edge_dr[x];
+    }
+    return CT_OK;
+}
+
+}  // extern "C"

@@ -105,6 +105,52 @@ int ct_reward_from_series_host(ct_engine *eng, const uint8_t *h_series, int32_t 
 /* Kernel launches issued by this engine since creation (bench.py's gpu_launches). */
 int64_t ct_engine_launch_count(ct_engine *eng);
 
+/* ---------------------------------------------------------------------------------------------
+ * Native host side of the batched MCTS scheduler (csrc/native_tree.cpp): bit-packed
+ * SimpleNetworkGrammar states and the tree statistics.  Each entry cites what it replaces:
+ *   get_actions / do_action / get_unique_state   reference circuitree/models.py:164-270, :337-400
+ *   select_and_expand + rollout + visit backprop reference circuitree/circuitree.py:315-384, :218-246, :468-482
+ *   backpropagate_reward                         reference circuitree/circuitree.py:484-499
+ *   mark_as_exhausted                            reference circuitree/circuitree.py:386-420
+ *   grow_tree                                    reference circuitree/circuitree.py:539-586
+ * The random stream is numpy's PCG64 (state handed over by the caller), consumed exactly like
+ * Generator.shuffle / Generator.choice in the reference, so trees are identical for identical rewards.
+ * Scope: root holds every component (sorted, e.g. "ABC::"), <= 5 components, <= 3 interaction types.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ct_tree ct_tree;
+
+const char *ct_tree_last_error(void);
+/* components / types: one character per component / interaction type, in declaration order.
+ * max_interactions < 0 means n*n; n_exhausted = NaN means "never exhaust" (Python None). */
+int ct_tree_create(const char *components, const char *types, int32_t max_interactions, const char *root,
+                   double exploration_constant, double n_exhausted, ct_tree **out);
+int ct_tree_destroy(ct_tree *t);
+/* numpy Generator(PCG64).bit_generator.state: 128-bit state and inc as (lo, hi) words. */
+int ct_tree_set_rng(ct_tree *t, const uint64_t state[2], const uint64_t inc[2], int32_t has_uint32, uint32_t uinteger);
+int ct_tree_get_rng(ct_tree *t, uint64_t state[2], uint64_t inc[2], int32_t *has_uint32, uint32_t *uinteger);
+/* table[v] = log(v) as the caller's numpy computes it (keeps UCB scores bit-identical to numpy). */
+int ct_tree_set_log_table(ct_tree *t, const double *table, int64_t n);
+int ct_tree_rng_draw(ct_tree *t, int32_t kind, int64_t n, int64_t *out);
+/* k MCTS selections under virtual loss; returns 100 with n_done < k when the tree is exhausted. */
+int ct_tree_select(ct_tree *t, int32_t k, uint64_t *sim_keys, uint64_t *sim_handles, int32_t *n_done);
+int ct_tree_backprop(ct_tree *t, int32_t k, const double *rewards);
+int ct_tree_pending(ct_tree *t, int32_t *n_pending, int32_t *lengths, int32_t *ids);
+int ct_tree_size(ct_tree *t, int64_t *n_nodes, int64_t *n_edges);
+int ct_tree_export(ct_tree *t, uint64_t *node_keys, int64_t *node_visits, double *node_reward, uint8_t *node_exhausted,
+                   int32_t *edge_parent, int32_t *edge_child, int64_t *edge_visits, double *edge_reward);
+int ct_tree_key_to_string(ct_tree *t, uint64_t key, char *buf, int32_t buflen);
+int ct_tree_string_to_key(ct_tree *t, const char *s, int32_t canonical, uint64_t *key);
+int ct_tree_actions(ct_tree *t, uint64_t key, int32_t *ids, int32_t cap, int32_t *n_out);
+int ct_tree_do_action(ct_tree *t, uint64_t key, int32_t action, uint64_t *out);
+int ct_tree_key_to_handle(ct_tree *t, uint64_t key, uint64_t *handle);
+int ct_tree_grow(ct_tree *t);
+/* Root-parallel merge across GPUs: sparse (state key, d visits, d reward) records. */
+int ct_tree_collect_deltas(ct_tree *t, int64_t *n_node_recs, uint64_t *node_key, int64_t *node_dv, double *node_dr,
+                           int64_t *n_edge_recs, uint64_t *edge_pkey, uint64_t *edge_ckey, int64_t *edge_dv, double *edge_dr);
+int ct_tree_merge_deltas(ct_tree *t, int64_t n_node_recs, const uint64_t *node_key, const int64_t *node_dv,
+                         const double *node_dr, int64_t n_edge_recs, const uint64_t *edge_pkey, const uint64_t *edge_ckey,
+                         const int64_t *edge_dv, const double *edge_dr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,203 @@
+"""Native (C++) grammar + MCTS scheduler vs the reference's golden vectors and vs the Python mirror.
+
+Everything here runs on the CPU: the native tree is host code inside libcircuitree_b200.so.
+Covers SURVEY.md section 8 rows a4-a10, a12 for the batched scheduler: bit-exact state strings,
+action order, canonical forms, RNG consumption, tree statistics and exhaustion bookkeeping.
+"""
+import hashlib
+import zlib
+
+import numpy as np
+import pytest
+
+from circuitree_b200 import CircuiTree, SimpleNetworkGrammar
+from circuitree_b200.native import NativeExhaustionError, NativeTree
+
+AI = ["activates", "inhibits"]
+
+
+def crc_reward(state: str) -> float:
+    return (zlib.crc32(state.encode()) % 1000) / 1000.0
+
+
+def crc_rewards(states):
+    return [crc_reward(s) for s in states]
+
+
+def step_digest(path, sim_node, reward):
+    return zlib.crc32(("|".join(path) + "#" + sim_node + "#" + f"{reward:.12g}").encode())
+
+
+def graph_digest(graph):
+    h = hashlib.sha256()
+    for n in sorted(graph.nodes):
+        a = graph.nodes[n]
+        h.update(f"{n}|{a.get('visits')}|{float(a.get('reward')):.12g}|{int(bool(a.get('is_exhausted', False)))}\n".encode())
+    for u, v in sorted(graph.edges):
+        a = graph.edges[u, v]
+        h.update(f"{u}>{v}|{a.get('visits')}|{float(a.get('reward')):.12g}\n".encode())
+    return h.hexdigest()
+
+
+def grammar(n):
+    return SimpleNetworkGrammar(list("ABCDE"[:n]), AI)
+
+
+def native(n, root, seed, n_exhausted=np.inf, c=None, **kw):
+    return NativeTree(grammar(n), root, seed=seed, n_exhausted=n_exhausted, exploration_constant=c, reward_fn=crc_rewards, **kw)
+
+
+def test_rng_matches_numpy_generator():
+    t = native(3, "ABC::", 123)
+    rg = np.random.default_rng(123)
+    from circuitree_b200.native import _lib, _check
+    import ctypes
+
+    sizes = [18, 17, 2, 3, 5, 50, 7, 1, 33, 64, 65, 100, 2, 2, 9]
+    for rep in range(40):
+        for n in sizes:
+            if (rep + n) % 3 == 0:
+                ref = list(range(n)); rg.shuffle(ref)
+                out = np.zeros(n, dtype=np.int64)
+                _check(_lib().ct_tree_rng_draw(t._h, 0, n, out.ctypes.data))
+                assert out.tolist() == ref
+            else:
+                ref = int(rg.choice(np.arange(n)))
+                out = np.zeros(1, dtype=np.int64)
+                _check(_lib().ct_tree_rng_draw(t._h, 1, n, out.ctypes.data))
+                assert int(out[0]) == ref
+    t._pull_rng()
+    assert t.rg.bit_generator.state == rg.bit_generator.state
+
+
+def test_actions_and_unique_state_match_reference(ref_vectors):
+    t3, t5 = native(3, "ABC::", 0), native(5, "ABCDE::", 0)
+    for state, actions in ref_vectors["actions3"].items():
+        assert t3.get_actions(state) == actions, state
+    for state, actions in ref_vectors["actions5"].items():
+        assert t5.get_actions(state) == actions, state
+    t4 = native(4, "ABCD::", 0)
+    for state, unique in ref_vectors["unique"].items():
+        n = len(state.strip("*").split("::")[0])
+        t = {3: t3, 4: t4, 5: t5}[n]
+        assert t.get_unique_state(state) == unique, state
+    tm = NativeTree(SimpleNetworkGrammar(list("ABC"), AI, max_interactions=4), "ABC::", seed=0, reward_fn=crc_rewards)
+    for state, actions in ref_vectors["actions3_max4"].items():
+        assert tm.get_actions(state) == actions, state
+
+
+def test_declaration_order_is_respected():
+    g = SimpleNetworkGrammar(["C", "A", "B"], ["inhibits", "activates"])
+    t = NativeTree(g, "ABC::", seed=0, reward_fn=crc_rewards)
+    for s in ["ABC::", "ABC::CAi", "ABC::ABa_BCi", "ABC::AAa_ABi_BBa"]:
+        assert t.get_actions(s) == g.get_actions(s), s
+
+
+@pytest.mark.parametrize("key,n,root,steps,seed,n_exh,c", [
+    ("mcts3", 3, "ABC::", 3000, 0, np.inf, None),
+    ("mcts3_c05", 3, "ABC::", 500, 7, np.inf, 0.5),
+    ("mcts5", 5, "ABCDE::", 150, 1, np.inf, None),
+    ("mcts2_exhaust", 2, "AB::", 5000, 3, 3, None),
+    ("mcts3_exhaust", 3, "ABC::", 2500, 5, 2, None),
+])
+def test_native_mcts_trace_is_bit_exact(ref_vectors, key, n, root, steps, seed, n_exh, c):
+    gold = ref_vectors[key]
+    t = native(n, root, seed, n_exh, c)
+    digests, err = [], None
+    try:
+        t.search_mcts(steps, batch_size=1, callback=lambda tr, i, p, s, r: digests.append(step_digest(p, s, r)))
+    except NativeExhaustionError:
+        err = "ExhaustionError"
+    assert digests == gold["digests"][: len(digests)]
+    assert len(digests) == gold["n_done"]
+    assert err == gold["error"]
+    g = t.to_networkx()
+    assert (g.number_of_nodes(), g.number_of_edges()) == (gold["n_nodes"], gold["n_edges"])
+    assert graph_digest(g) == gold["graph_digest"]
+    assert g.nodes[root]["visits"] == gold["root_visits"] and g.nodes[root]["reward"] == gold["root_reward"]
+
+
+class CrcTree(CircuiTree):
+    def get_reward(self, state, **kw):
+        return crc_reward(state)
+
+
+@pytest.mark.parametrize("batch", [7, 64])
+def test_native_batched_equals_python_batched(batch):
+    """Virtual-loss batching: same leaves, same statistics, same RNG state as the Python scheduler."""
+    py = CrcTree(grammar=grammar(4), root="ABCD::", seed=9, n_exhausted=np.inf)
+    py.search_mcts_batched(600, batch)
+    nt = native(4, "ABCD::", 9)
+    nt.search_mcts(600, batch_size=batch)
+    assert graph_digest(nt.to_networkx()) == graph_digest(py.graph)
+    assert nt.rg.bit_generator.state == py.rg.bit_generator.state
+
+
+def test_native_grow_tree(simple3_space):
+    t = native(3, "ABC::", 0)
+    t.grow_tree()
+    g = t.to_networkx()
+    nodes = sorted(g.nodes)
+    assert nodes == simple3_space["nodes"]
+    index = {n: i for i, n in enumerate(nodes)}
+    assert sorted([index[u], index[v]] for u, v in g.edges) == simple3_space["edges"]
+
+
+def test_four_component_space_size():
+    t = native(4, "ABCD::", 0)
+    t.grow_tree()
+    nn, ne = t.size()
+    keys = t.export()["node_keys"]
+    n_term = int(((keys >> np.uint64(62)) & np.uint64(1)).sum())
+    assert nn == 2 * n_term + 1          # every non-root state has exactly one terminal twin
+    assert n_term > 100_000
+    # spot-check canonical forms against the Python grammar
+    g4 = grammar(4)
+    rg = np.random.default_rng(0)
+    for k in rg.choice(keys, size=300, replace=False):
+        s = t.key_to_string(int(k))
+        assert g4.get_unique_state(s) == s
+
+
+def test_handles_match_compile_topology():
+    from circuitree_b200 import _capi
+
+    t = native(3, "ABC::", 0)
+    for s in ["*ABC::ABi_BCi_CAi", "*ABC::AAa_BAi_CCa", "*ABC::ABa"]:
+        comps, act, inh = SimpleNetworkGrammar.parse_genotype(s)
+        assert t.handle_of_key(t.string_to_key(s)) == _capi.compile_topology(3, act, inh)
+
+
+def test_delta_merge_equals_single_tree_sums():
+    """Root-parallel merge semantics: after exchanging deltas every replica holds the sum of all
+    replicas' increments on every node and edge."""
+    reps = [native(3, "ABC::", s) for s in (1, 2, 3)]
+    for rounds in range(3):
+        for r in reps:
+            r.search_mcts(200, batch_size=16)
+        deltas = [r.collect_deltas() for r in reps]
+        for i, r in enumerate(reps):
+            for j, d in enumerate(deltas):
+                if i != j:
+                    r.merge_deltas(d)
+    digs = {graph_digest(r.to_networkx()) for r in reps}
+    g = reps[0].to_networkx()
+    assert g.nodes["ABC::"]["visits"] == 3 * 3 * 200
+    # replicas agree on visits everywhere; rewards agree up to summation order
+    g1 = reps[1].to_networkx()
+    assert sorted(g.nodes) == sorted(g1.nodes)
+    for n in g.nodes:
+        assert g.nodes[n]["visits"] == g1.nodes[n]["visits"]
+        assert abs(g.nodes[n]["reward"] - g1.nodes[n]["reward"]) < 1e-9
+    assert len(digs) <= 3
+
+
+def test_unsupported_configurations_are_refused():
+    from circuitree_b200 import _capi
+
+    with pytest.raises(_capi.EngineError):
+        NativeTree(SimpleNetworkGrammar(list("ABC"), AI), "AB::", seed=0, reward_fn=crc_rewards)      # partial root
+    with pytest.raises(_capi.EngineError):
+        NativeTree(SimpleNetworkGrammar(list("ABCDEF"), AI), "ABCDEF::", seed=0, reward_fn=crc_rewards)
+    with pytest.raises(_capi.EngineError):
+        NativeTree(SimpleNetworkGrammar(list("ABC"), AI, fixed_components=["A"]), "ABC::", seed=0, reward_fn=crc_rewards)
