@@ -145,6 +145,9 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-traj", type=int, default=4096, help="trajectories of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mcts-batch", type=int, default=16384, help="leaves per reward launch in the MCTS leg")
+    ap.add_argument("--mcts-batches", type=int, default=2)
+    ap.add_argument("--mcts-traj", type=int, default=16, help="SSA trajectories per rollout in the MCTS leg")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -237,13 +240,35 @@ def main() -> None:
     h2d = n * _capi.N_PARAMS * 4 + 32 + 8
     d2h = n * 8 + 16
 
+    # ---- second half of the metric: MCTS rollouts/s (BASELINE config 1/4 shape) -------------------
+    # Root-parallel search on the 3-component grammar: native selection under virtual loss, one reward
+    # launch per batch of leaves (grouped by topology), per-rank trees merged by a sparse all-gather.
+    from circuitree_b200.native import NativeTree
+    from circuitree_b200.parallel import RootParallelSearch
+
+    mcts_B, mcts_K, mcts_batches = args.mcts_traj, args.mcts_batch, args.mcts_batches
+    tree = NativeTree(grammar, "ABC::", seed=1000 + rank, n_exhausted=np.inf, trajectories_per_reward=mcts_B,
+                      device=local_rank, reward_seed=77 + rank)
+    search = RootParallelSearch(tree, sync_every=mcts_K * mcts_batches, batch_size=mcts_K,
+                                device=dev if world > 1 else None)
+    tree.search_mcts(min(mcts_K, 1024), batch_size=min(mcts_K, 1024))        # warm-up
+    ev0 = tree.reward_engine.total_events
+    barrier()
+    t0 = time.perf_counter()
+    search.run(mcts_K * mcts_batches)
+    barrier()
+    mcts_secs = time.perf_counter() - t0
+    mcts_events = tree.reward_engine.total_events - ev0
+    mcts_launches = tree.reward_engine.engine.launch_count
+
     # ---- reduce over ranks: max time, summed events ----
-    stats = torch.tensor([kernel_ms, e2e_secs, float(total_events), float(e2e_events)], dtype=torch.float64, device=dev)
+    stats = torch.tensor([kernel_ms, e2e_secs, float(total_events), float(e2e_events), mcts_secs, float(mcts_events)],
+                         dtype=torch.float64, device=dev)
     if world > 1:
         mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        kernel_ms, e2e_secs = float(mx[0]), float(mx[1])
-        total_events, e2e_events = float(sm[2]), float(sm[3])
+        kernel_ms, e2e_secs, mcts_secs = float(mx[0]), float(mx[1]), float(mx[4])
+        total_events, e2e_events, mcts_events = float(sm[2]), float(sm[3]), float(sm[5])
     value = total_events / (kernel_ms * 1e-3)
     e2e_value = e2e_events / e2e_secs
 
@@ -267,13 +292,20 @@ def main() -> None:
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "RewardEngine.run -> ct_rewards_host (explicit host parameter vectors)"},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches),   # SSA kernel launches inside the timed region of `value`
             "roofline": {"bound": "alu_issue", "achieved": achieved, "peak": peak, "unit": "Tlane-instr/s",
                          "frac": achieved / peak, "traffic": None,
                          "note": f"algorithmic {i_step(n_react, n_spec):.1f} issue slots/step (DESIGN.md) x steps/s per GPU; "
                                  f"peak = {n_sm} SMs x 128 lanes x {sm_max:.0f} MHz; HBM traffic per launch is "
                                  f"~{(n * 12) / 1e6:.0f} MB of outputs (see profiles/)"},
             "mean_reward": mean_reward, "wall_s_timed_region": wall,
+            "mcts": {"metric": "mcts_rollouts_per_s", "value": world * mcts_K * mcts_batches / mcts_secs, "unit": "rollouts/s",
+                     "reaction_steps_per_s": mcts_events / mcts_secs,
+                     "config": {"workload": "root-parallel MCTS, SimpleNetworkGrammar ABC (activates/inhibits), "
+                                            f"{mcts_batches} batches x {mcts_K} leaves per rank, {mcts_B} SSA trajectories "
+                                            "per rollout, leaves grouped by topology, one sparse stats merge per rank",
+                                "n_exhausted": "inf", "tree_nodes_rank0": tree.size()[0],
+                                "merge_bytes_rank0": search.bytes_exchanged}},
         }
         if not args.no_cpu_baseline:
             from oracle import ssa_oracle

@@ -31,6 +31,7 @@ class SimConfig(ctypes.Structure):
         ("decim", ctypes.c_int32),
         ("dt", ctypes.c_float),
         ("init_mean", ctypes.c_float),
+        ("schedule", ctypes.c_int32),
         ("ranges", (ctypes.c_float * 3) * N_PARAMS),
     ]
 

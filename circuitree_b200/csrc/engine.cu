@@ -43,20 +43,21 @@ struct ct_engine {
     int device = 0;
     int n_sm = 0;
     cudaStream_t stream = nullptr;   // used by the host-buffer entry points
-    KernelInfo k3, k4, k5;
+    KernelInfo k3, k4, k5;          // uniform-topology warps
+    KernelInfo m3, m4, m5;          // mixed-topology warps
     int64_t launches = 0;
 };
 
 namespace {
 
-template <int MM>
+template <int MM, bool kMixed>
 int prepare_kernel(KernelInfo& ki)
 {
     ki.smem = (size_t)ct::kThreads * MM * ct::kSerStride + (ct::kThreads / 32) * ct::kSerStride * sizeof(float);
-    CT_CUDA(cudaFuncSetAttribute(ct::ssa_pairwise_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
-    CT_CUDA(cudaFuncSetAttribute(ct::ssa_pairwise_kernel<MM>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    CT_CUDA(cudaFuncSetAttribute(ct::ssa_pairwise_kernel<MM, kMixed>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
+    CT_CUDA(cudaFuncSetAttribute(ct::ssa_pairwise_kernel<MM, kMixed>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared));
-    CT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.blocks_per_sm, ct::ssa_pairwise_kernel<MM>, ct::kThreads,
+    CT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.blocks_per_sm, ct::ssa_pairwise_kernel<MM, kMixed>, ct::kThreads,
                                                           ki.smem));
     if (ki.blocks_per_sm < 1) return fail(CT_ERR_CUDA, "SSA kernel (M=%d) does not fit on an SM", MM);
     return CT_OK;
@@ -69,6 +70,7 @@ int validate_cfg(const ct_sim_config* cfg)
     if (cfg->nt / cfg->decim > CT_MAX_NDEC) return fail(CT_ERR_INVALID, "nt/decim = %d exceeds CT_MAX_NDEC", cfg->nt / cfg->decim);
     if (!(cfg->dt > 0.0f)) return fail(CT_ERR_INVALID, "dt must be positive");
     if (!(cfg->init_mean >= 0.0f) || cfg->init_mean > 80.0f) return fail(CT_ERR_INVALID, "init_mean out of range [0, 80]");
+    if (cfg->schedule < 0 || cfg->schedule > 2) return fail(CT_ERR_INVALID, "schedule must be 0 (auto), 1 (uniform) or 2 (mixed)");
     return CT_OK;
 }
 
@@ -90,6 +92,7 @@ int ct_default_config(ct_sim_config* cfg)
     cfg->decim = 16;
     cfg->dt = 20.0f;
     cfg->init_mean = 10.0f;
+    cfg->schedule = 0;
     memcpy(cfg->ranges, r, sizeof r);
     return CT_OK;
 }
@@ -114,9 +117,12 @@ int ct_engine_create(int device, ct_engine** out)
     eng->n_sm = prop.multiProcessorCount;
     CT_CUDA(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
     int rc;
-    if ((rc = prepare_kernel<3>(eng->k3)) != CT_OK) { delete eng; return rc; }
-    if ((rc = prepare_kernel<4>(eng->k4)) != CT_OK) { delete eng; return rc; }
-    if ((rc = prepare_kernel<5>(eng->k5)) != CT_OK) { delete eng; return rc; }
+    if ((rc = prepare_kernel<3, false>(eng->k3)) != CT_OK) { delete eng; return rc; }
+    if ((rc = prepare_kernel<4, false>(eng->k4)) != CT_OK) { delete eng; return rc; }
+    if ((rc = prepare_kernel<5, false>(eng->k5)) != CT_OK) { delete eng; return rc; }
+    if ((rc = prepare_kernel<3, true>(eng->m3)) != CT_OK) { delete eng; return rc; }
+    if ((rc = prepare_kernel<4, true>(eng->m4)) != CT_OK) { delete eng; return rc; }
+    if ((rc = prepare_kernel<5, true>(eng->m5)) != CT_OK) { delete eng; return rc; }
     *out = eng;
     return CT_OK;
 }
@@ -233,16 +239,19 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
     A.dt = cfg->dt;
     A.init_mean = cfg->init_mean;
 
-    const KernelInfo& ki = max_nsp <= 3 ? eng->k3 : (max_nsp == 4 ? eng->k4 : eng->k5);
+    // schedule: big jobs -> one topology per warp (uniform branches); many small jobs -> mixed lanes
+    bool mixed = cfg->schedule == 2;
+    if (cfg->schedule == 0) mixed = n_jobs > 1 && total / (uint64_t)n_jobs < 2048;
+    const KernelInfo& ki = mixed ? (max_nsp <= 3 ? eng->m3 : (max_nsp == 4 ? eng->m4 : eng->m5))
+                                 : (max_nsp <= 3 ? eng->k3 : (max_nsp == 4 ? eng->k4 : eng->k5));
     uint64_t want_blocks = (total + ct::kThreads - 1) / ct::kThreads;
     uint64_t max_blocks = (uint64_t)eng->n_sm * ki.blocks_per_sm;
     const unsigned grid = (unsigned)(want_blocks < max_blocks ? want_blocks : max_blocks);
-    if (max_nsp <= 3)
-        ct::ssa_pairwise_kernel<3><<<grid, ct::kThreads, ki.smem, stream>>>(A);
-    else if (max_nsp == 4)
-        ct::ssa_pairwise_kernel<4><<<grid, ct::kThreads, ki.smem, stream>>>(A);
-    else
-        ct::ssa_pairwise_kernel<5><<<grid, ct::kThreads, ki.smem, stream>>>(A);
+#define CT_LAUNCH(MM, MIXED) ct::ssa_pairwise_kernel<MM, MIXED><<<grid, ct::kThreads, ki.smem, stream>>>(A)
+    if (max_nsp <= 3) { if (mixed) CT_LAUNCH(3, true); else CT_LAUNCH(3, false); }
+    else if (max_nsp == 4) { if (mixed) CT_LAUNCH(4, true); else CT_LAUNCH(4, false); }
+    else { if (mixed) CT_LAUNCH(5, true); else CT_LAUNCH(5, false); }
+#undef CT_LAUNCH
     CT_CUDA(cudaGetLastError());
     eng->launches += 1;
     CT_CUDA(cudaFreeAsync(d_jobs, stream));

@@ -339,7 +339,11 @@ __device__ __forceinline__ void lane_init(Lane<MM>& L, const LaunchArgs& A, cons
     L.ctr = 0;
 }
 
-template <int MM>
+// kMixed = false: a warp runs one topology at a time (uniform edge branches; a tile with another
+// topology waits until the warp has drained) -- best for big jobs.  kMixed = true: every lane carries
+// its own topology, tiles are handed out without draining -- best for MCTS batches of many small jobs.
+// Results are identical in both modes.
+template <int MM, bool kMixed>
 __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa_pairwise_kernel(const LaunchArgs A)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -353,7 +357,7 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa
     lane_park<MM>(L);
     L.k = 0; L.kd = 0; L.dcount = 1; L.events = 0; L.ctr = 0; L.traj_lo = L.traj_hi = 0; L.out = 0;
     bool active = false, finished = false;
-    uint32_t topo_lo = 0, topo_hi = 0;   // warp-uniform copies of the topology code (see below)
+    uint32_t topo_lo = 0, topo_hi = 0;   // uniform mode: the warp's topology; mixed mode: this lane's topology
     // warp-uniform tile state
     Job job;                        // job of the current tile
     job.topo = 0; job.traj_base = 0; job.n_traj = 0; job.out_offset = 0; job.tile_start = 0; job.pad = 0;
@@ -375,10 +379,11 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa
                 fin &= fin - 1;
                 float rw; int lg;
                 const uint8_t* sser = warp_ser + (size_t)src * (MM * kSerStride);
-                warp_reward(sser, z, nsp, A.n_dec, lane, rw, lg);
+                const int nsp_src = kMixed ? (int)((__shfl_sync(kFull, topo_hi, src) >> 24) & 15u) : nsp;
+                warp_reward(sser, z, nsp_src, A.n_dec, lane, rw, lg);
                 const uint32_t out = __shfl_sync(kFull, L.out, src);
                 if (A.series) {
-                    for (int s = 0; s < nsp; ++s)
+                    for (int s = 0; s < nsp_src; ++s)
                         for (int k = lane; k < A.n_dec; k += 32)
                             A.series[(size_t)out * A.series_stride + s * A.n_dec + k] = sser[s * kSerStride + k];
                 }
@@ -399,6 +404,7 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa
                     if (take) {
                         lane_init<MM>(L, A, job, pos + rank, nsp);
                         active = true;
+                        if (kMixed) { topo_lo = (uint32_t)topo; topo_hi = (uint32_t)(topo >> 32); }
                     }
                     const uint32_t n_need = __popc(need);
                     pos += (n_need < avail) ? n_need : avail;
@@ -428,15 +434,11 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa
                 if (have_pending) {
                     const bool same = (pend.topo == topo);
                     const bool drained = (__ballot_sync(kFull, active) == 0u);
-                    if (same || drained) {
+                    if (kMixed || same || drained) {
                         job = pend; pos = pend_pos; end = pend_end;
                         topo = job.topo;
-                        // Rebuild the code from one bit per lane: a vote result is warp-uniform by
-                        // construction, so the compiler can keep it in uniform registers and turn the
-                        // edge tests of ssa_step into uniform branches.
-                        topo_lo = (uint32_t)topo;
-                        topo_hi = (uint32_t)(topo >> 32);
-                        nsp = (int)((topo_hi >> 24) & 15u);
+                        nsp = (int)topo_nspecies(topo);
+                        if (!kMixed) { topo_lo = (uint32_t)topo; topo_hi = (uint32_t)(topo >> 32); }
                         have_pending = false;
                         continue;
                     }
@@ -451,8 +453,8 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa
         L.ctr += 1;
         // A warp-wide OR of identical values: the result is warp-uniform by construction, which lets
         // the compiler keep the topology in uniform registers and branch uniformly on its bits.
-        const uint32_t u_lo = __reduce_or_sync(kFull, topo_lo);
-        const uint32_t u_hi = __reduce_or_sync(kFull, topo_hi);
+        const uint32_t u_lo = kMixed ? topo_lo : __reduce_or_sync(kFull, topo_lo);
+        const uint32_t u_hi = kMixed ? topo_hi : __reduce_or_sync(kFull, topo_hi);
         const int u_nsp = (int)((u_hi >> 24) & 15u);
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
@@ -462,7 +464,7 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa
                 if (!alive) {
                     active = false;
                     finished = true;
-                    lane_park<MM>(L);
+                    lane_park<MM>(L);   // (mixed mode keeps topo_hi: the reward stage needs the species count)
                 }
             }
         }

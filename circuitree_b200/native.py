@@ -223,23 +223,33 @@ class NativeTree:
         if self.reward_fn is not None:
             return np.asarray(self.reward_fn([self.key_to_string(int(k)) for k in keys]), dtype=np.float64)
         eng = self.reward_engine
-        # group leaves by topology: one job per distinct simulated state
+        # group leaves by topology: one job per distinct simulated state ...
         uniq, inverse, counts = np.unique(handles, return_inverse=True, return_counts=True)
-        n_traj = (counts * self.trajectories_per_reward).astype(np.uint32)
+        # ... launched longest-expected-first (events per trajectory seen so far for that topology;
+        # unseen topologies first), which shortens the tail of a launch with few trajectories per lane
+        cost = np.array([eng.cost.get(int(h), np.inf) for h in uniq])
+        order = np.argsort(-cost, kind="stable")
+        rank_of = np.empty_like(order)
+        rank_of[order] = np.arange(len(order))
+        B = self.trajectories_per_reward
+        n_traj = (counts[order] * B).astype(np.uint32)
         offsets = np.concatenate(([0], np.cumsum(n_traj, dtype=np.uint64)[:-1])).astype(np.uint64)
         bases = offsets + np.uint64(eng.next_traj)
         eng.next_traj += int(n_traj.sum())
-        out = eng.engine.rewards_host(uniq, n_traj, bases, eng.cfg, eng.seed, per_trajectory=True)
+        out = eng.engine.rewards_host(uniq[order], n_traj, bases, eng.cfg, eng.seed, per_trajectory=True)
         eng.total_events += int(out["job_events"].sum())
         eng.total_trajectories += int(n_traj.sum())
+        for h, ev, nt in zip(uniq[order], out["job_events"], n_traj):
+            eng.cost[int(h)] = float(ev) / float(nt)
         # leaf x of topology u gets the mean of its own block of trajectories_per_reward trajectories
         per = out["reward"].astype(np.float64)
+        block_means = per.reshape(-1, B).mean(axis=1)
+        first_block = (offsets // np.uint64(B)).astype(np.int64)
         rewards = np.zeros(len(keys), dtype=np.float64)
         taken = np.zeros(len(uniq), dtype=np.int64)
-        B = self.trajectories_per_reward
         for x, u in enumerate(inverse):
-            start = int(offsets[u]) + int(taken[u]) * B
-            rewards[x] = per[start: start + B].mean()
+            j = rank_of[u]
+            rewards[x] = block_means[first_block[j] + taken[u]]
             taken[u] += 1
         return rewards
 

@@ -39,6 +39,7 @@ class RewardEngine:
         self.next_traj = 0           # trajectory ids handed out so far (fresh Philox streams per call)
         self.total_events = 0
         self.total_trajectories = 0
+        self.cost: dict[int, float] = {}   # topology handle -> events per trajectory observed so far
 
     @property
     def engine(self) -> _capi.Engine:

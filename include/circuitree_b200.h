@@ -38,6 +38,8 @@ typedef struct ct_sim_config {
     int32_t decim;           /* grid points per stored block, default 16; nt/decim <= CT_MAX_NDEC */
     float dt;                /* seconds between grid points, default 20 */
     float init_mean;         /* Poisson mean of initial protein counts, default 10 */
+    int32_t schedule;        /* 0 auto; 1 one topology per warp (big jobs); 2 mixed topologies per warp
+                                (many small jobs).  Results are identical, only the speed differs. */
     float ranges[CT_N_PARAMS][3]; /* (lo, hi, is_log) per parameter, SPEC.md section 4 */
 } ct_sim_config;
 

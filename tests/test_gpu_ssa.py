@@ -190,6 +190,26 @@ def test_mixed_topology_batch_equals_separate_launches(eng):
         assert np.array_equal(mixed["events"][off[j]:off[j + 1]], single["events"]), s
 
 
+def test_schedules_give_identical_results(eng):
+    """One topology per warp (schedule 1) vs mixed topologies per warp (schedule 2): same bits."""
+    rg = np.random.default_rng(3)
+    pool = ["*ABC::ABi_BCi_CAi", "*ABC::ABa_BCi_CAa", "*ABC::AAi_BBi_CCi", "*AB::ABa_BAi", "*ABC::", "*ABC::ABi_BAi_CCa_ACa"]
+    states = [pool[i] for i in rg.integers(0, len(pool), size=150)]
+    counts = rg.integers(1, 40, size=150)
+    bases = np.arange(150) * 1000
+    outs = []
+    for schedule in (1, 2, 0):
+        c = small_cfg(nt=320, decim=16)
+        c.schedule = schedule
+        outs.append(gpu_run(eng, states, counts, c, seed=13, bases=bases))
+    for k in ("reward", "lag", "events"):
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+        assert np.array_equal(outs[0][k], outs[2][k]), k
+    bad = _capi.default_config(); bad.schedule = 7
+    with pytest.raises(_capi.EngineError):
+        eng.rewards_host([handle_of("*AB::ABi")], [4], [0], bad, 1)
+
+
 def test_empty_and_ragged_jobs(eng):
     c = small_cfg(nt=160, decim=16)
     out = eng.rewards_host([handle_of("*AB::ABi"), handle_of("*AB::ABa"), handle_of("*AB::ABi")], [0, 3, 0], [0, 0, 0], c, 1,
