@@ -32,7 +32,7 @@ WORKER = textwrap.dedent("""
     out = {"rank": rank, "root_visits": g.nodes["ABC::"]["visits"], "digest": h.hexdigest(), "syncs": search.n_syncs,
            "nodes": g.number_of_nodes(), "bytes": search.bytes_exchanged,
            "edge_sum": sum(g.edges["ABC::", c]["visits"] for c in g.successors("ABC::"))}
-    print("RESULT " + json.dumps(out), flush=True)
+    open(os.path.join(os.environ["CT_TEST_OUT"], f"rank{rank}.json"), "w").write(json.dumps(out))
     dist.destroy_process_group()
 """) % str(ROOT)
 
@@ -40,15 +40,14 @@ WORKER = textwrap.dedent("""
 def test_root_parallel_merge_world2(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1", CT_TEST_OUT=str(tmp_path))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29517", str(script)]
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
     import json
 
-    results = [json.loads(line.split("RESULT ", 1)[1]) for line in res.stdout.splitlines() if "RESULT " in line]
-    assert len(results) == 2
+    results = [json.loads((tmp_path / f"rank{r}.json").read_text()) for r in range(2)]
     a, b = sorted(results, key=lambda r: r["rank"])
     # both replicas hold the sum of both ranks' work and agree on every statistic
     assert a["root_visits"] == b["root_visits"] == 512
