@@ -145,8 +145,9 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-traj", type=int, default=4096, help="trajectories of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mcts-batch", type=int, default=16384, help="leaves per reward launch in the MCTS leg")
-    ap.add_argument("--mcts-batches", type=int, default=2)
+    ap.add_argument("--mcts-batch", type=int, default=8192, help="leaves per reward launch in the MCTS leg")
+    ap.add_argument("--mcts-batches", type=int, default=6)
+    ap.add_argument("--mcts-depth", type=int, default=3, help="reward batches in flight (virtual loss)")
     ap.add_argument("--mcts-traj", type=int, default=16, help="SSA trajectories per rollout in the MCTS leg")
     args = ap.parse_args()
 
@@ -250,8 +251,9 @@ def main() -> None:
     tree = NativeTree(grammar, "ABC::", seed=1000 + rank, n_exhausted=np.inf, trajectories_per_reward=mcts_B,
                       device=local_rank, reward_seed=77 + rank)
     search = RootParallelSearch(tree, sync_every=mcts_K * mcts_batches, batch_size=mcts_K,
-                                device=dev if world > 1 else None)
+                                device=dev if world > 1 else None, pipeline_depth=args.mcts_depth)
     tree.search_mcts(min(mcts_K, 1024), batch_size=min(mcts_K, 1024))        # warm-up
+    tree.timing = {k: 0.0 for k in tree.timing}
     ev0 = tree.reward_engine.total_events
     barrier()
     t0 = time.perf_counter()
@@ -303,8 +305,10 @@ def main() -> None:
                      "reaction_steps_per_s": mcts_events / mcts_secs,
                      "config": {"workload": "root-parallel MCTS, SimpleNetworkGrammar ABC (activates/inhibits), "
                                             f"{mcts_batches} batches x {mcts_K} leaves per rank, {mcts_B} SSA trajectories "
-                                            "per rollout, leaves grouped by topology, one sparse stats merge per rank",
+                                            "per rollout, leaves grouped by topology, "
+                                            f"{args.mcts_depth} reward batches in flight, one sparse stats merge per rank",
                                 "n_exhausted": "inf", "tree_nodes_rank0": tree.size()[0],
+                                "host_seconds_rank0": {k: round(v, 3) for k, v in tree.timing.items()},
                                 "merge_bytes_rank0": search.bytes_exchanged}},
         }
         if not args.no_cpu_baseline:

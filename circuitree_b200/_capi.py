@@ -15,7 +15,10 @@ N_PARAMS = 10
 MAX_SPECIES = 5
 MAX_NDEC = 126
 
-_LIB_PATH = Path(__file__).resolve().parent / "libcircuitree_b200.so"
+import os as _os
+
+# CIRCUITREE_B200_LIB selects another build of the same library (kernel-variant experiments only)
+_LIB_PATH = Path(_os.environ.get("CIRCUITREE_B200_LIB") or Path(__file__).resolve().parent / "libcircuitree_b200.so")
 _lib: Optional[ctypes.CDLL] = None
 
 
@@ -32,6 +35,7 @@ class SimConfig(ctypes.Structure):
         ("dt", ctypes.c_float),
         ("init_mean", ctypes.c_float),
         ("schedule", ctypes.c_int32),
+        ("lpt", ctypes.c_int32),
         ("ranges", (ctypes.c_float * 3) * N_PARAMS),
     ]
 
@@ -73,15 +77,19 @@ def lib() -> ctypes.CDLL:
     L.ct_engine_destroy.argtypes = [vp]
     L.ct_engine_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]
     L.ct_compile_topology.argtypes = [i32, vp, i32, vp, i32, i32, ctypes.POINTER(u64)]
-    L.ct_launch_rewards.argtypes = [vp, vp, vp, vp, i32, ctypes.POINTER(SimConfig), u64, vp, vp, vp, vp, vp, vp, i32]
+    L.ct_launch_rewards.argtypes = [vp, vp, vp, vp, vp, i32, ctypes.POINTER(SimConfig), u64, vp, vp, vp, vp, vp, vp, i32]
     L.ct_reduce_jobs.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
-    L.ct_rewards_host.argtypes = [vp, vp, vp, vp, i32, ctypes.POINTER(SimConfig), u64, vp, vp, vp, vp, vp]
+    L.ct_rewards_host.argtypes = [vp, vp, vp, vp, vp, i32, ctypes.POINTER(SimConfig), u64, vp, vp, vp, vp, vp]
     L.ct_reward_from_series_host.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    L.ct_rewards_submit.argtypes = [vp, vp, vp, vp, vp, i32, ctypes.POINTER(SimConfig), u64, vp, ctypes.POINTER(i64)]
+    L.ct_rewards_wait.argtypes = [vp, i64, vp, vp, vp, vp]
     L.ct_engine_launch_count.restype = i64
     L.ct_engine_launch_count.argtypes = [vp]
+    L.ct_engine_warp_iterations.restype = i64
+    L.ct_engine_warp_iterations.argtypes = [vp]
     for name in ("ct_default_config", "ct_engine_create", "ct_engine_destroy", "ct_engine_info",
                  "ct_compile_topology", "ct_launch_rewards", "ct_reduce_jobs", "ct_rewards_host",
-                 "ct_reward_from_series_host"):
+                 "ct_reward_from_series_host", "ct_rewards_submit", "ct_rewards_wait"):
         getattr(L, name).restype = ctypes.c_int
     _lib = L
     return L
@@ -140,6 +148,10 @@ class Engine:
         except Exception:
             pass
 
+    def warp_iterations(self) -> int:
+        """Debug counter, see ``ct_engine_warp_iterations``."""
+        return int(lib().ct_engine_warp_iterations(self._h))
+
     @property
     def launch_count(self) -> int:
         return int(lib().ct_engine_launch_count(self._h))
@@ -147,12 +159,14 @@ class Engine:
     # -- device-buffer path (torch tensors are only buffers: pass tensor.data_ptr()) --------------
     def launch_rewards(self, handles: np.ndarray, n_traj: np.ndarray, traj_base: np.ndarray, cfg: SimConfig,
                        seed: int, stream: int, d_reward: int, d_lag: int = 0, d_events: int = 0,
-                       d_params: int = 0, d_series: int = 0, series_stride: int = 0) -> None:
+                       d_params: int = 0, d_series: int = 0, series_stride: int = 0, job_cost=None) -> None:
         handles = np.ascontiguousarray(handles, dtype=np.uint64)
         n_traj = np.ascontiguousarray(n_traj, dtype=np.uint32)
         traj_base = np.ascontiguousarray(traj_base, dtype=np.uint64)
+        if job_cost is not None:
+            job_cost = np.ascontiguousarray(job_cost, dtype=np.float32)
         check(lib().ct_launch_rewards(self._h, handles.ctypes.data, n_traj.ctypes.data, traj_base.ctypes.data,
-                                      len(handles), ctypes.byref(cfg), seed, stream or None, d_params or None,
+                                      _ptr(job_cost), len(handles), ctypes.byref(cfg), seed, stream or None, d_params or None,
                                       d_reward or None, d_lag or None, d_events or None, d_series or None,
                                       series_stride))
 
@@ -164,7 +178,7 @@ class Engine:
 
     # -- host-buffer path ---------------------------------------------------------------------------
     def rewards_host(self, handles: Sequence[int], n_traj: Sequence[int], traj_base: Sequence[int], cfg: SimConfig,
-                     seed: int, params: Optional[np.ndarray] = None, per_trajectory: bool = False):
+                     seed: int, params: Optional[np.ndarray] = None, per_trajectory: bool = False, job_cost=None):
         handles = np.ascontiguousarray(handles, dtype=np.uint64)
         n_traj = np.ascontiguousarray(n_traj, dtype=np.uint32)
         traj_base = np.ascontiguousarray(traj_base, dtype=np.uint64)
@@ -176,9 +190,42 @@ class Engine:
         lag = np.zeros(total, dtype=np.int32) if per_trajectory else None
         if params is not None:
             params = np.ascontiguousarray(params, dtype=np.float32).reshape(total, N_PARAMS)
-        check(lib().ct_rewards_host(self._h, handles.ctypes.data, n_traj.ctypes.data, traj_base.ctypes.data, n_jobs,
+        if job_cost is not None:
+            job_cost = np.ascontiguousarray(job_cost, dtype=np.float32)
+        check(lib().ct_rewards_host(self._h, handles.ctypes.data, n_traj.ctypes.data, traj_base.ctypes.data, _ptr(job_cost), n_jobs,
                                     ctypes.byref(cfg), seed, _ptr(params), job_mean.ctypes.data,
                                     job_events.ctypes.data, _ptr(reward), _ptr(lag)))
+        out = {"job_mean": job_mean, "job_events": job_events}
+        if per_trajectory:
+            out["reward"] = reward
+            out["lag"] = lag
+        return out
+
+    def submit(self, handles, n_traj, traj_base, cfg: SimConfig, seed: int, params: Optional[np.ndarray] = None,
+               job_cost=None) -> dict:
+        """Asynchronous ``rewards_host``: returns a ticket dict to pass to :meth:`wait`."""
+        handles = np.ascontiguousarray(handles, dtype=np.uint64)
+        n_traj = np.ascontiguousarray(n_traj, dtype=np.uint32)
+        traj_base = np.ascontiguousarray(traj_base, dtype=np.uint64)
+        total = int(n_traj.sum())
+        if params is not None:
+            params = np.ascontiguousarray(params, dtype=np.float32).reshape(total, N_PARAMS)
+        if job_cost is not None:
+            job_cost = np.ascontiguousarray(job_cost, dtype=np.float32)
+        ticket = ctypes.c_int64(0)
+        check(lib().ct_rewards_submit(self._h, handles.ctypes.data, n_traj.ctypes.data, traj_base.ctypes.data,
+                                      _ptr(job_cost), len(handles), ctypes.byref(cfg), seed, _ptr(params),
+                                      ctypes.byref(ticket)))
+        return {"ticket": int(ticket.value), "n_jobs": len(handles), "total": total, "params": params}
+
+    def wait(self, ticket: dict, per_trajectory: bool = False) -> dict:
+        n_jobs, total = ticket["n_jobs"], ticket["total"]
+        job_mean = np.zeros(n_jobs, dtype=np.float64)
+        job_events = np.zeros(n_jobs, dtype=np.uint64)
+        reward = np.zeros(total, dtype=np.float32) if per_trajectory else None
+        lag = np.zeros(total, dtype=np.int32) if per_trajectory else None
+        check(lib().ct_rewards_wait(self._h, ticket["ticket"], job_mean.ctypes.data, job_events.ctypes.data,
+                                    _ptr(reward), _ptr(lag)))
         out = {"job_mean": job_mean, "job_events": job_events}
         if per_trajectory:
             out["reward"] = reward

@@ -2,10 +2,12 @@
 // tables, stream-ordered scratch, kernel launches.  No CPU fallback: without a CUDA device every
 // compute entry point fails with CT_ERR_NO_DEVICE / CT_ERR_CUDA.
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <vector>
 
 #include "../../include/circuitree_b200.h"
@@ -39,13 +41,29 @@ struct KernelInfo {
 
 }  // namespace
 
+namespace {
+struct Ticket {                      // one asynchronous reward batch in flight
+    cudaStream_t stream = nullptr;
+    int32_t n_jobs = 0;
+    uint64_t total = 0;
+    float *d_params = nullptr, *d_reward = nullptr;
+    int32_t* d_lag = nullptr;
+    uint32_t* d_events = nullptr;
+    double* d_mean = nullptr;
+    uint64_t* d_jev = nullptr;
+};
+}  // namespace
+
 struct ct_engine {
     int device = 0;
+    std::map<int64_t, Ticket> tickets;
+    int64_t next_ticket = 1;
     int n_sm = 0;
     cudaStream_t stream = nullptr;   // used by the host-buffer entry points
     KernelInfo k3, k4, k5;          // uniform-topology warps
     KernelInfo m3, m4, m5;          // mixed-topology warps
     int64_t launches = 0;
+    unsigned long long* d_warp_iters = nullptr;   // debug counter (ct_engine_warp_iterations)
 };
 
 namespace {
@@ -71,6 +89,7 @@ int validate_cfg(const ct_sim_config* cfg)
     if (!(cfg->dt > 0.0f)) return fail(CT_ERR_INVALID, "dt must be positive");
     if (!(cfg->init_mean >= 0.0f) || cfg->init_mean > 80.0f) return fail(CT_ERR_INVALID, "init_mean out of range [0, 80]");
     if (cfg->schedule < 0 || cfg->schedule > 2) return fail(CT_ERR_INVALID, "schedule must be 0 (auto), 1 (uniform) or 2 (mixed)");
+    if (cfg->lpt < 0 || cfg->lpt > 1) return fail(CT_ERR_INVALID, "lpt must be 0 or 1");
     return CT_OK;
 }
 
@@ -93,6 +112,7 @@ int ct_default_config(ct_sim_config* cfg)
     cfg->dt = 20.0f;
     cfg->init_mean = 10.0f;
     cfg->schedule = 0;
+    cfg->lpt = 1;
     memcpy(cfg->ranges, r, sizeof r);
     return CT_OK;
 }
@@ -131,6 +151,10 @@ int ct_engine_destroy(ct_engine* eng)
 {
     if (!eng) return CT_OK;
     cudaSetDevice(eng->device);
+    for (auto& kv : eng->tickets) {
+        cudaStreamSynchronize(kv.second.stream);
+        cudaStreamDestroy(kv.second.stream);
+    }
     if (eng->stream) cudaStreamDestroy(eng->stream);
     delete eng;
     return CT_OK;
@@ -145,6 +169,24 @@ int ct_engine_info(ct_engine* eng, int32_t* n_sm, int32_t* resident_lanes)
 }
 
 int64_t ct_engine_launch_count(ct_engine* eng) { return eng ? eng->launches : -1; }
+
+// Debug: total hot-loop iterations (two lock-step SSA steps of 32 lanes each) of all warps since the
+// previous call; the first call switches the counter on.  lane utilisation = events / (64 * value).
+int64_t ct_engine_warp_iterations(ct_engine* eng)
+{
+    if (!eng) return -1;
+    cudaSetDevice(eng->device);
+    if (!eng->d_warp_iters) {
+        if (cudaMalloc((void**)&eng->d_warp_iters, sizeof(unsigned long long)) != cudaSuccess) return -1;
+        cudaMemset(eng->d_warp_iters, 0, sizeof(unsigned long long));
+        return 0;
+    }
+    unsigned long long v = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpy(&v, eng->d_warp_iters, sizeof v, cudaMemcpyDeviceToHost);
+    cudaMemset(eng->d_warp_iters, 0, sizeof v);
+    return (int64_t)v;
+}
 
 int ct_compile_topology(int32_t n_species, const int64_t* act, int32_t n_act, const int64_t* inh, int32_t n_inh,
                         int32_t k, uint64_t* handle)
@@ -173,8 +215,9 @@ int ct_compile_topology(int32_t n_species, const int64_t* act, int32_t n_act, co
 }
 
 int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n_traj, const uint64_t* traj_base,
-                      int32_t n_jobs, const ct_sim_config* cfg, uint64_t seed, void* stream_, const float* d_params,
-                      float* d_reward, int32_t* d_lag, uint32_t* d_events, uint8_t* d_series, int32_t series_stride)
+                      const float* job_cost, int32_t n_jobs, const ct_sim_config* cfg, uint64_t seed, void* stream_,
+                      const float* d_params, float* d_reward, int32_t* d_lag, uint32_t* d_events, uint8_t* d_series,
+                      int32_t series_stride)
 {
     if (!eng) return fail(CT_ERR_INVALID, "engine is NULL");
     if (n_jobs < 0 || (n_jobs && (!handles || !n_traj || !traj_base))) return fail(CT_ERR_INVALID, "bad job arrays");
@@ -233,6 +276,9 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
     }
     A.seed_lo = (uint32_t)seed;
     A.seed_hi = (uint32_t)(seed >> 32);
+    A.total = (uint32_t)total;
+    A.order = nullptr;
+    A.warp_iters = eng->d_warp_iters;
     A.nt = cfg->nt;
     A.decim = cfg->decim;
     A.n_dec = cfg->nt / cfg->decim;
@@ -242,6 +288,35 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
     // schedule: big jobs -> one topology per warp (uniform branches); many small jobs -> mixed lanes
     bool mixed = cfg->schedule == 2;
     if (cfg->schedule == 0) mixed = n_jobs > 1 && total / (uint64_t)n_jobs < 2048;
+    if (mixed) A.n_tiles = (uint32_t)((total + ct::kTile - 1) / ct::kTile);   // tiles over launch positions
+
+    // longest-expected-first order (cfg->lpt): cost pre-pass + radix sort of (job, cost) keys
+    unsigned long long *d_keys = nullptr, *d_keys_out = nullptr;
+    uint32_t *d_slots = nullptr, *d_order = nullptr;
+    float* d_job_cost = nullptr;
+    void* d_tmp = nullptr;
+    if (cfg->lpt && total > 1) {
+        CT_CUDA(cudaMallocAsync((void**)&d_keys, sizeof(unsigned long long) * total, stream));
+        CT_CUDA(cudaMallocAsync((void**)&d_keys_out, sizeof(unsigned long long) * total, stream));
+        CT_CUDA(cudaMallocAsync((void**)&d_slots, sizeof(uint32_t) * total, stream));
+        CT_CUDA(cudaMallocAsync((void**)&d_order, sizeof(uint32_t) * total, stream));
+        if (job_cost) {
+            CT_CUDA(cudaMallocAsync((void**)&d_job_cost, sizeof(float) * n_jobs, stream));
+            CT_CUDA(cudaMemcpyAsync(d_job_cost, job_cost, sizeof(float) * n_jobs, cudaMemcpyHostToDevice, stream));
+        }
+        ct::cost_key_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(A, d_job_cost, mixed ? 0 : 1, d_keys, d_slots);
+        CT_CUDA(cudaGetLastError());
+        int end_bit = 32;
+        if (!mixed) { int b = 0; while ((1ll << b) < (long long)n_jobs) ++b; end_bit = 32 + b; }
+        size_t tmp_bytes = 0;
+        CT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys_out, d_slots, d_order, (int)total, 0,
+                                                end_bit, stream));
+        CT_CUDA(cudaMallocAsync(&d_tmp, tmp_bytes ? tmp_bytes : 1, stream));
+        CT_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys_out, d_slots, d_order, (int)total, 0,
+                                                end_bit, stream));
+        eng->launches += 2;
+        A.order = d_order;
+    }
     const KernelInfo& ki = mixed ? (max_nsp <= 3 ? eng->m3 : (max_nsp == 4 ? eng->m4 : eng->m5))
                                  : (max_nsp <= 3 ? eng->k3 : (max_nsp == 4 ? eng->k4 : eng->k5));
     uint64_t want_blocks = (total + ct::kThreads - 1) / ct::kThreads;
@@ -256,6 +331,11 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
     eng->launches += 1;
     CT_CUDA(cudaFreeAsync(d_jobs, stream));
     CT_CUDA(cudaFreeAsync(d_counter, stream));
+    if (d_keys) {
+        cudaFreeAsync(d_keys, stream); cudaFreeAsync(d_keys_out, stream); cudaFreeAsync(d_slots, stream);
+        cudaFreeAsync(d_order, stream); cudaFreeAsync(d_tmp, stream);
+        if (d_job_cost) cudaFreeAsync(d_job_cost, stream);
+    }
     return CT_OK;
 }
 
@@ -285,8 +365,8 @@ int ct_reduce_jobs(ct_engine* eng, const uint32_t* n_traj, int32_t n_jobs, void*
 }
 
 int ct_rewards_host(ct_engine* eng, const uint64_t* handles, const uint32_t* n_traj, const uint64_t* traj_base,
-                    int32_t n_jobs, const ct_sim_config* cfg, uint64_t seed, const float* h_params, double* h_job_mean,
-                    uint64_t* h_job_events, float* h_reward, int32_t* h_lag)
+                    const float* job_cost, int32_t n_jobs, const ct_sim_config* cfg, uint64_t seed, const float* h_params,
+                    double* h_job_mean, uint64_t* h_job_events, float* h_reward, int32_t* h_lag)
 {
     if (!eng) return fail(CT_ERR_INVALID, "engine is NULL");
     if (n_jobs < 0 || (n_jobs && (!handles || !n_traj || !traj_base))) return fail(CT_ERR_INVALID, "bad job arrays");
@@ -313,8 +393,8 @@ int ct_rewards_host(ct_engine* eng, const uint64_t* handles, const uint32_t* n_t
         CT_CUDA(cudaMallocAsync((void**)&d_params, sizeof(float) * total * CT_N_PARAMS, s));
         CT_CUDA(cudaMemcpyAsync(d_params, h_params, sizeof(float) * total * CT_N_PARAMS, cudaMemcpyHostToDevice, s));
     }
-    int rc = ct_launch_rewards(eng, handles, n_traj, traj_base, n_jobs, cfg, seed, s, d_params, d_reward, d_lag,
-                               d_events, nullptr, 0);
+    int rc = ct_launch_rewards(eng, handles, n_traj, traj_base, job_cost, n_jobs, cfg, seed, s, d_params, d_reward,
+                               d_lag, d_events, nullptr, 0);
     if (rc == CT_OK) rc = ct_reduce_jobs(eng, n_traj, n_jobs, s, d_reward, d_events, d_mean, d_jev);
     if (rc == CT_OK) {
         if (h_job_mean) CT_CUDA(cudaMemcpyAsync(h_job_mean, d_mean, sizeof(double) * n_jobs, cudaMemcpyDeviceToHost, s));
@@ -331,6 +411,72 @@ int ct_rewards_host(ct_engine* eng, const uint64_t* handles, const uint32_t* n_t
     cudaError_t e = cudaStreamSynchronize(s);
     if (rc != CT_OK) return rc;
     if (e != cudaSuccess) return fail(CT_ERR_CUDA, "kernel execution failed: %s", cudaGetErrorString(e));
+    return CT_OK;
+}
+
+// Asynchronous pair: submit enqueues the batch on a stream of its own and returns at once, so
+// the kernels of consecutive batches overlap (the tail of one launch -- a few long trajectories --
+// runs next to the body of the following one).  wait copies the results out and releases the ticket.
+int ct_rewards_submit(ct_engine* eng, const uint64_t* handles, const uint32_t* n_traj, const uint64_t* traj_base,
+                      const float* job_cost, int32_t n_jobs, const ct_sim_config* cfg, uint64_t seed, const float* h_params,
+                      int64_t* ticket)
+{
+    if (!eng || !ticket) return fail(CT_ERR_INVALID, "engine or ticket is NULL");
+    if (n_jobs < 1 || !handles || !n_traj || !traj_base) return fail(CT_ERR_INVALID, "bad job arrays");
+    CT_CUDA(cudaSetDevice(eng->device));
+    Ticket t;
+    t.n_jobs = n_jobs;
+    for (int j = 0; j < n_jobs; ++j) t.total += n_traj[j];
+    if (t.total == 0) return fail(CT_ERR_INVALID, "empty batch");
+    CT_CUDA(cudaStreamCreateWithFlags(&t.stream, cudaStreamNonBlocking));
+    cudaStream_t s = t.stream;
+    CT_CUDA(cudaMallocAsync((void**)&t.d_reward, sizeof(float) * t.total, s));
+    CT_CUDA(cudaMallocAsync((void**)&t.d_lag, sizeof(int32_t) * t.total, s));
+    CT_CUDA(cudaMallocAsync((void**)&t.d_events, sizeof(uint32_t) * t.total, s));
+    CT_CUDA(cudaMallocAsync((void**)&t.d_mean, sizeof(double) * n_jobs, s));
+    CT_CUDA(cudaMallocAsync((void**)&t.d_jev, sizeof(uint64_t) * n_jobs, s));
+    if (h_params) {
+        CT_CUDA(cudaMallocAsync((void**)&t.d_params, sizeof(float) * t.total * CT_N_PARAMS, s));
+        CT_CUDA(cudaMemcpyAsync(t.d_params, h_params, sizeof(float) * t.total * CT_N_PARAMS, cudaMemcpyHostToDevice, s));
+    }
+    int rc = ct_launch_rewards(eng, handles, n_traj, traj_base, job_cost, n_jobs, cfg, seed, s, t.d_params, t.d_reward,
+                               t.d_lag, t.d_events, nullptr, 0);
+    if (rc == CT_OK) rc = ct_reduce_jobs(eng, n_traj, n_jobs, s, t.d_reward, t.d_events, t.d_mean, t.d_jev);
+    if (rc != CT_OK) {
+        cudaStreamSynchronize(s);
+        cudaStreamDestroy(s);
+        return rc;
+    }
+    *ticket = eng->next_ticket++;
+    eng->tickets[*ticket] = t;
+    return CT_OK;
+}
+
+int ct_rewards_wait(ct_engine* eng, int64_t ticket, double* h_job_mean, uint64_t* h_job_events, float* h_reward,
+                    int32_t* h_lag)
+{
+    if (!eng) return fail(CT_ERR_INVALID, "engine is NULL");
+    auto it = eng->tickets.find(ticket);
+    if (it == eng->tickets.end()) return fail(CT_ERR_INVALID, "unknown ticket %lld", (long long)ticket);
+    Ticket t = it->second;
+    eng->tickets.erase(it);
+    CT_CUDA(cudaSetDevice(eng->device));
+    cudaStream_t s = t.stream;
+    cudaError_t e = cudaSuccess, e2;
+    if (h_job_mean && (e2 = cudaMemcpyAsync(h_job_mean, t.d_mean, sizeof(double) * t.n_jobs, cudaMemcpyDeviceToHost, s))) e = e2;
+    if (h_job_events && (e2 = cudaMemcpyAsync(h_job_events, t.d_jev, sizeof(uint64_t) * t.n_jobs, cudaMemcpyDeviceToHost, s))) e = e2;
+    if (h_reward && (e2 = cudaMemcpyAsync(h_reward, t.d_reward, sizeof(float) * t.total, cudaMemcpyDeviceToHost, s))) e = e2;
+    if (h_lag && (e2 = cudaMemcpyAsync(h_lag, t.d_lag, sizeof(int32_t) * t.total, cudaMemcpyDeviceToHost, s))) e = e2;
+    cudaFreeAsync(t.d_reward, s);
+    cudaFreeAsync(t.d_lag, s);
+    cudaFreeAsync(t.d_events, s);
+    cudaFreeAsync(t.d_mean, s);
+    cudaFreeAsync(t.d_jev, s);
+    if (t.d_params) cudaFreeAsync(t.d_params, s);
+    e2 = cudaStreamSynchronize(s);
+    if (e2 != cudaSuccess) e = e2;
+    cudaStreamDestroy(s);
+    if (e != cudaSuccess) return fail(CT_ERR_CUDA, "asynchronous reward batch failed: %s", cudaGetErrorString(e));
     return CT_OK;
 }
 

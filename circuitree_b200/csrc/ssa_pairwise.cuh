@@ -1,6 +1,6 @@
 // Batched Gillespie SSA + in-kernel oscillation reward for the pairwise TF-network model
 // (SPEC.md sections 2-8).  One trajectory per lane, one topology per warp at a time, persistent
-// warps that pull 64-trajectory tiles off a global counter and refill lanes as trajectories end.
+// warps that pull 32-trajectory tiles off a global counter and refill lanes as trajectories end.
 // The per-trajectory record (M x n_dec companded bytes) lives in shared memory and is reduced to
 // (reward, lag) by the whole warp with shuffles when the lane finishes; it never reaches HBM.
 //
@@ -15,7 +15,7 @@
 namespace ct {
 
 constexpr int kThreads = 128;        // 4 warps per CTA
-constexpr int kTile = 64;            // trajectories per tile
+constexpr int kTile = 32;            // trajectories per tile (one per lane: finest longest-first granularity)
 constexpr int kSerStride = 128;      // bytes per species per lane (>= n_dec)
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kTopoStride = 5;       // edge (i,j) sits at bits 2*(i*5+j) of the topology code
@@ -42,6 +42,9 @@ struct LaunchArgs {
     uint32_t* events;                // nullable
     uint8_t* series;                 // nullable debug dump [total][series_stride]
     int32_t series_stride;
+    unsigned long long* warp_iters;  // nullable debug counter: hot-loop iterations (2 steps each) summed over warps
+    const uint32_t* order;           // nullable: launch position -> output slot, longest expected first
+    uint32_t total;                  // trajectories in the launch
     float rng_lo[10];
     float rng_span[10];
     uint32_t log_mask;
@@ -55,6 +58,18 @@ __host__ __device__ __forceinline__ uint32_t topo_edge(uint64_t topo, int i, int
     return (uint32_t)(topo >> (2 * (i * kTopoStride + j))) & 3u;
 }
 __host__ __device__ __forceinline__ uint32_t topo_nspecies(uint64_t topo) { return (uint32_t)(topo >> 56) & 15u; }
+// handle -> (presence mask | nsp << 28, activation mask), one bit per cell c = i*5+j
+__host__ __device__ __forceinline__ void topo_masks(uint64_t topo, uint32_t& pres, uint32_t& actm)
+{
+    uint32_t p = 0, a = 0;
+    for (int c = 0; c < 25; ++c) {
+        const uint32_t e = (uint32_t)(topo >> (2 * c)) & 3u;
+        p |= (e != 0u ? 1u : 0u) << c;
+        a |= (e == 1u ? 1u : 0u) << c;
+    }
+    pres = p | (topo_nspecies(topo) << 28);
+    actm = a;
+}
 
 // ---- warp-cooperative reward (SPEC.md section 7) ---------------------------------------------
 // ser: the finished lane's record [nsp][kSerStride] bytes in shared memory; z: per-warp scratch
@@ -165,46 +180,68 @@ __device__ __forceinline__ float compand_block(float s)
     return fminf(floorf(sqrtf(s) + 0.5f), 255.0f);
 }
 
+#ifndef CT_EDGE_BRANCH
+#define CT_EDGE_BRANCH 1     // 1: absent edges are skipped by (warp-uniform) branches; 0: compiler's choice
+#endif
+#ifndef CT_GENE_CHAINS
+#define CT_GENE_CHAINS 0     // 1: one running sum per gene (shorter chains, measured 6 % slower); 0: one global chain
+#endif
+#if CT_EDGE_BRANCH
+#define CT_KEEP_BRANCH() asm volatile("")
+#else
+#define CT_KEEP_BRANCH()
+#endif
+
 // One SSA step (SPEC.md section 2) executed by ALL lanes of the warp in lock-step; lanes without a
 // trajectory carry zero rates (a0 = 0: nothing fires, nothing is recorded), which keeps the hot
-// loop convergent so the topology tests below are warp-uniform branches.  `topo_lo/topo_hi/nsp`
-// must be warp-uniform.  Returns false for a lane that has just recorded its last grid sample.
+// loop convergent so the topology tests below are warp-uniform branches in uniform mode.
+// `pres` has bit c = i*5+j set when edge i->j exists, `actm` when it activates; species count nsp.
+// Returns false for a lane that has just recorded its last grid sample.
+//
+// Selection: s_r = [t < c_r] is monotone along a running sum, so reaction r fires iff
+// s_r - s_{r-1} = 1 and the state updates are differences of neighbouring s values; a reaction with
+// zero propensity has c_r = c_{r-1} and can never fire.  With CT_GENE_CHAINS every gene has its own
+// running sum lc (from 0) and compares t_j = target - (sum of the previous genes' totals) against
+// it; float rounding at a gene boundary can at worst make the step fire no reaction or one
+// reaction in each of two neighbouring genes (probability ~1e-7 per step), never an impossible one.
 template <int MM>
-__device__ __forceinline__ bool ssa_step(Lane<MM>& L, const bool active, const uint32_t topo_lo,
-                                         const uint32_t topo_hi, const int nsp, uint32_t w_tau, uint32_t w_sel,
-                                         uint8_t* ser, const int nt, const int decim, const float dt)
+__device__ __forceinline__ bool ssa_step(Lane<MM>& L, const bool active, const uint32_t pres, const uint32_t actm,
+                                         const int nsp, uint32_t w_tau, uint32_t w_sel, uint8_t* ser, const int nt,
+                                         const int decim, const float dt)
 {
-    auto edge = [&](int i, int j) -> uint32_t {
-        const int sh = 2 * (i * kTopoStride + j);
-        return sh < 32 ? (topo_lo >> sh) & 3u : (topo_hi >> (sh - 32)) & 3u;
-    };
-    // ---- propensities as a running sum in SPEC order; cum[r] is the sum up to reaction r ----
+    auto has = [&](int i, int j) -> bool { return (pres >> (i * kTopoStride + j)) & 1u; };
+    auto is_act = [&](int i, int j) -> bool { return (actm >> (i * kTopoStride + j)) & 1u; };
+    // ---- propensities as running sums in SPEC order ----
     float cum[4 * MM + 2 * MM * MM];
+    float off[MM + 1];
     float c = 0.0f;
+    off[0] = 0.0f;
 #pragma unroll
     for (int j = 0; j < MM; ++j) {
+        if (CT_GENE_CHAINS) c = 0.0f;
         if (j < nsp) {
             const float n = L.n[j], na = L.A[j];
             const float km_a = (na > 0.0f) ? L.km1 : L.km0;
             const float km_i = (na > 0.0f) ? L.km3 : L.km2;
             c += (n > na) ? km_i : km_a;     cum[4 * j + 0] = c;
-            c += L.gm * L.R[j];              cum[4 * j + 1] = c;
-            c += L.kp * L.R[j];              cum[4 * j + 2] = c;
-            c += L.gp * L.P[j];              cum[4 * j + 3] = c;
+            c = fmaf(L.gm, L.R[j], c);       cum[4 * j + 1] = c;
+            c = fmaf(L.kp, L.R[j], c);       cum[4 * j + 2] = c;
+            c = fmaf(L.gp, L.P[j], c);       cum[4 * j + 3] = c;
             const float koff = (n >= 2.0f) ? L.k_off2 : L.k_off1;
             const float kfree = L.k_on * (2.0f - n);
 #pragma unroll
             for (int i = 0; i < MM; ++i) {
-                if (edge(i, j)) {
-                    asm volatile("");   // keep this a (warp-uniform) branch, not predicated code
+                if (has(i, j)) {
+                    CT_KEEP_BRANCH();
                     const int r = 4 * MM + 2 * (j * MM + i);
-                    c += kfree * L.P[i];     cum[r] = c;
-                    c += koff * L.b[i][j];   cum[r + 1] = c;
+                    c = fmaf(kfree, L.P[i], c);     cum[r] = c;
+                    c = fmaf(koff, L.b[i][j], c);   cum[r + 1] = c;
                 }
             }
         }
+        if (CT_GENE_CHAINS) off[j + 1] = off[j] + c;
     }
-    const float a0 = c;
+    const float a0 = CT_GENE_CHAINS ? off[MM] : c;
 
     // ---- time to next event; grid samples crossed keep the pre-event state ----
     const float tau = (-0.69314718056f * fast_log2(u01(w_tau))) * fast_rcp(a0);   // a0 == 0 -> +inf
@@ -228,33 +265,33 @@ __device__ __forceinline__ bool ssa_step(Lane<MM>& L, const bool active, const u
         if (L.k >= nt) return false;
     }
 
-    // ---- select and fire: s_r = [target < cum_r] is monotone in r, so reaction r fires iff
-    //      s_r - s_{r-1} = 1; no reaction fires when a0 = 0 or rounding leaves target >= a0 ----
+    // ---- select and fire ----
     const float target = u01(w_sel) * a0;
     float s_prev = 0.0f;
 #pragma unroll
     for (int j = 0; j < MM; ++j) {
         if (j < nsp) {
-            const float s_tx = (target < cum[4 * j + 0]) ? 1.0f : 0.0f;
-            const float s_rm = (target < cum[4 * j + 1]) ? 1.0f : 0.0f;
-            const float s_tl = (target < cum[4 * j + 2]) ? 1.0f : 0.0f;
-            const float s_dp = (target < cum[4 * j + 3]) ? 1.0f : 0.0f;
+            const float t = CT_GENE_CHAINS ? target - off[j] : target;
+            if (CT_GENE_CHAINS) s_prev = (t < 0.0f) ? 1.0f : 0.0f;
+            const float s_tx = (t < cum[4 * j + 0]) ? 1.0f : 0.0f;
+            const float s_rm = (t < cum[4 * j + 1]) ? 1.0f : 0.0f;
+            const float s_tl = (t < cum[4 * j + 2]) ? 1.0f : 0.0f;
+            const float s_dp = (t < cum[4 * j + 3]) ? 1.0f : 0.0f;
             L.R[j] += fmaf(2.0f, s_tx, -s_prev) - s_rm;
             L.P[j] += fmaf(2.0f, s_tl, -s_rm) - s_dp;
             s_prev = s_dp;
 #pragma unroll
             for (int i = 0; i < MM; ++i) {
-                const uint32_t e = edge(i, j);
-                if (e) {
-                    asm volatile("");
+                if (has(i, j)) {
+                    CT_KEEP_BRANCH();
                     const int r = 4 * MM + 2 * (j * MM + i);
-                    const float s_b = (target < cum[r]) ? 1.0f : 0.0f;
-                    const float s_u = (target < cum[r + 1]) ? 1.0f : 0.0f;
+                    const float s_b = (t < cum[r]) ? 1.0f : 0.0f;
+                    const float s_u = (t < cum[r + 1]) ? 1.0f : 0.0f;
                     const float d = fmaf(2.0f, s_b, -s_prev) - s_u;   // +1 bind, -1 unbind
                     L.b[i][j] += d;
                     L.P[i] -= d;
                     L.n[j] += d;
-                    if (e == 1u) L.A[j] += d;
+                    if (is_act(i, j)) L.A[j] += d;
                     s_prev = s_u;
                 }
             }
@@ -278,18 +315,19 @@ __device__ __forceinline__ void lane_park(Lane<MM>& L)
     L.t_rem = 0.0f;
 }
 
-// Start trajectory `idx` of `job` on this lane (SPEC.md sections 3-5).
-template <int MM>
-__device__ __forceinline__ void lane_init(Lane<MM>& L, const LaunchArgs& A, const Job& job, uint32_t idx, int nsp)
+// Parameter vector of one trajectory (SPEC.md sections 3-4): explicit if given, else sampled.
+__device__ __forceinline__ void trajectory_params(const LaunchArgs& A, uint32_t traj_lo, uint32_t traj_hi, uint32_t out,
+                                                  float (&p)[12])
 {
-    const uint64_t traj = job.traj_base + idx;
-    L.traj_lo = (uint32_t)traj;
-    L.traj_hi = (uint32_t)(traj >> 32);
-    L.out = job.out_offset + idx;
-    float p[12];
+    if (A.params) {
+        const float* src = A.params + (size_t)out * 10;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) p[i] = src[i];
+        return;
+    }
 #pragma unroll
     for (int blk = 0; blk < 3; ++blk) {
-        Philox4 x = philox4x32_10(blk, 0u, L.traj_lo, L.traj_hi, A.seed_lo, A.seed_hi);
+        Philox4 x = philox4x32_10(blk, 0u, traj_lo, traj_hi, A.seed_lo, A.seed_hi);
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
             const int i = 4 * blk + w;
@@ -299,11 +337,59 @@ __device__ __forceinline__ void lane_init(Lane<MM>& L, const LaunchArgs& A, cons
             }
         }
     }
-    if (A.params) {
-        const float* src = A.params + (size_t)L.out * 10;
-#pragma unroll
-        for (int i = 0; i < 10; ++i) p[i] = src[i];
+}
+
+// last job whose out_offset <= slot (jobs are in output order; empty jobs never match a slot)
+__device__ __forceinline__ uint32_t job_of_slot(const LaunchArgs& A, uint32_t slot)
+{
+    uint32_t lo = 0, hi = A.n_jobs - 1;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (A.jobs[mid].out_offset <= slot) lo = mid; else hi = mid - 1;
     }
+    return lo;
+}
+
+// Pre-pass for longest-first scheduling: expected number of events of every trajectory, as a sort
+// key.  The event rate of an unregulated gene is 2 km (1 + kp/gm) (transcription, translation and
+// the two decays at steady state); job_cost[j] (nullable) scales it per topology, e.g. with the
+// events per trajectory the caller has observed for that topology.  Ascending key order =
+// descending cost; in uniform mode the job index is the major key so jobs stay contiguous.
+__global__ void cost_key_kernel(const LaunchArgs A, const float* job_cost, int job_major, unsigned long long* keys,
+                                uint32_t* slots)
+{
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= A.total) return;
+    const uint32_t j = job_of_slot(A, slot);
+    const Job job = A.jobs[j];
+    const uint64_t traj = job.traj_base + (slot - job.out_offset);
+    float p[12];
+    trajectory_params(A, (uint32_t)traj, (uint32_t)(traj >> 32), slot, p);
+    float cost = p[3] * (1.0f + p[7] / p[8]);
+    if (job_cost) cost *= job_cost[j];
+    if (!(cost >= 0.0f)) cost = 0.0f;                       // NaN / negative explicit parameters
+    const uint32_t bits = __float_as_uint(fminf(cost, 3.0e38f));
+    uint32_t low = 0xffffffffu - bits;
+    if (!job_major) {
+        // mixed-topology warps: bucket the cost by octave (sign + exponent) and sort by topology
+        // inside a bucket, so that neighbouring lanes mostly share their topology (less divergence)
+        const uint32_t h = (uint32_t)((job.topo * 0x9E3779B97F4A7C15ull) >> 41);          // 23 bits
+        low = ((0x1ffu - (bits >> 23)) << 23) | h;
+    }
+    keys[slot] = ((unsigned long long)(job_major ? j : 0u) << 32) | (unsigned long long)low;
+    slots[slot] = slot;
+}
+
+// Start trajectory `idx` of `job` on this lane (SPEC.md sections 3-5).
+template <int MM>
+__device__ __forceinline__ void lane_init(Lane<MM>& L, const LaunchArgs& A, const Job& job, uint32_t idx, int nsp)
+{
+    const uint64_t traj = job.traj_base + idx;
+    L.traj_lo = (uint32_t)traj;
+    L.traj_hi = (uint32_t)(traj >> 32);
+    L.out = job.out_offset + idx;
+    float p[12];
+    trajectory_params(A, L.traj_lo, L.traj_hi, L.out, p);
     L.k_on = p[0]; L.k_off1 = p[1]; L.k_off2 = p[2];
     L.km0 = p[3]; L.km1 = p[4]; L.km2 = p[5]; L.km3 = p[6];
     L.kp = p[7]; L.gm = p[8]; L.gp = p[9];
@@ -357,7 +443,9 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa
     lane_park<MM>(L);
     L.k = 0; L.kd = 0; L.dcount = 1; L.events = 0; L.ctr = 0; L.traj_lo = L.traj_hi = 0; L.out = 0;
     bool active = false, finished = false;
-    uint32_t topo_lo = 0, topo_hi = 0;   // uniform mode: the warp's topology; mixed mode: this lane's topology
+    // topology as two 25-bit masks + species count in bits 28..31 of `pres`
+    // (uniform mode: the warp's topology; mixed mode: this lane's topology)
+    uint32_t pres = 0, actm = 0;
     // warp-uniform tile state
     Job job;                        // job of the current tile
     job.topo = 0; job.traj_base = 0; job.n_traj = 0; job.out_offset = 0; job.tile_start = 0; job.pad = 0;
@@ -368,6 +456,7 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa
     uint32_t pend_pos = 0, pend_end = 0;
     uint64_t topo = 0;
     int nsp = 0;
+    unsigned long long n_iters = 0;
 
     for (;;) {
         const unsigned idle = __ballot_sync(kFull, !active);
@@ -379,7 +468,7 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa
                 fin &= fin - 1;
                 float rw; int lg;
                 const uint8_t* sser = warp_ser + (size_t)src * (MM * kSerStride);
-                const int nsp_src = kMixed ? (int)((__shfl_sync(kFull, topo_hi, src) >> 24) & 15u) : nsp;
+                const int nsp_src = kMixed ? (int)(__shfl_sync(kFull, pres, src) >> 28) : nsp;
                 warp_reward(sser, z, nsp_src, A.n_dec, lane, rw, lg);
                 const uint32_t out = __shfl_sync(kFull, L.out, src);
                 if (A.series) {
@@ -402,9 +491,20 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa
                     const uint32_t avail = end - pos;
                     const bool take = !active && (uint32_t)rank < avail;
                     if (take) {
-                        lane_init<MM>(L, A, job, pos + rank, nsp);
+                        if (kMixed) {
+                            // tiles are ranges of launch positions; every lane looks up its own job
+                            const uint32_t slot = A.order ? A.order[pos + rank] : pos + rank;
+                            const Job mine = A.jobs[job_of_slot(A, slot)];
+                            const int my_nsp = (int)topo_nspecies(mine.topo);
+                            lane_init<MM>(L, A, mine, slot - mine.out_offset, my_nsp);
+                            topo_masks(mine.topo, pres, actm);
+                        } else {
+                            // tiles are ranges of positions inside one job (jobs stay contiguous in `order`)
+                            const uint32_t p = job.out_offset + pos + rank;
+                            const uint32_t slot = A.order ? A.order[p] : p;
+                            lane_init<MM>(L, A, job, slot - job.out_offset, nsp);
+                        }
                         active = true;
-                        if (kMixed) { topo_lo = (uint32_t)topo; topo_hi = (uint32_t)(topo >> 32); }
                     }
                     const uint32_t n_need = __popc(need);
                     pos += (n_need < avail) ? n_need : avail;
@@ -418,6 +518,10 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa
                     t = __shfl_sync(kFull, t, 0);
                     if (t >= A.n_tiles) {
                         out_of_work = true;
+                    } else if (kMixed) {
+                        pend_pos = t * kTile;
+                        pend_end = min(pend_pos + (uint32_t)kTile, A.total);
+                        have_pending = true;
                     } else {
                         // binary search: last job with tile_start <= t
                         uint32_t lo = 0, hi = A.n_jobs - 1;
@@ -434,11 +538,16 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa
                 if (have_pending) {
                     const bool same = (pend.topo == topo);
                     const bool drained = (__ballot_sync(kFull, active) == 0u);
-                    if (kMixed || same || drained) {
+                    if (kMixed) {
+                        pos = pend_pos; end = pend_end;
+                        have_pending = false;
+                        continue;
+                    }
+                    if (same || drained) {
                         job = pend; pos = pend_pos; end = pend_end;
                         topo = job.topo;
                         nsp = (int)topo_nspecies(topo);
-                        if (!kMixed) { topo_lo = (uint32_t)topo; topo_hi = (uint32_t)(topo >> 32); }
+                        topo_masks(topo, pres, actm);
                         have_pending = false;
                         continue;
                     }
@@ -447,28 +556,30 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa
             }
             if (out_of_work && __ballot_sync(kFull, active) == 0u) break;
         }
+        ++n_iters;
 
         // two steps per Philox block (SPEC.md section 3); every lane runs them, parked lanes as no-ops
         const Philox4 x = philox4x32_10(L.ctr, 1u, L.traj_lo, L.traj_hi, A.seed_lo, A.seed_hi);
         L.ctr += 1;
         // A warp-wide OR of identical values: the result is warp-uniform by construction, which lets
         // the compiler keep the topology in uniform registers and branch uniformly on its bits.
-        const uint32_t u_lo = kMixed ? topo_lo : __reduce_or_sync(kFull, topo_lo);
-        const uint32_t u_hi = kMixed ? topo_hi : __reduce_or_sync(kFull, topo_hi);
-        const int u_nsp = (int)((u_hi >> 24) & 15u);
+        const uint32_t u_pres = kMixed ? pres : __reduce_or_sync(kFull, pres);
+        const uint32_t u_act = kMixed ? actm : __reduce_or_sync(kFull, actm);
+        const int u_nsp = (int)(u_pres >> 28);
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
-            const bool alive = ssa_step<MM>(L, active, u_lo, u_hi, u_nsp, h ? x.w[2] : x.w[0],
+            const bool alive = ssa_step<MM>(L, active, u_pres, u_act, u_nsp, h ? x.w[2] : x.w[0],
                                             h ? x.w[3] : x.w[1], ser, A.nt, A.decim, A.dt);
             if (__any_sync(kFull, !alive)) {   // rare, warp-uniform: keep the parking code off the hot path
                 if (!alive) {
                     active = false;
                     finished = true;
-                    lane_park<MM>(L);   // (mixed mode keeps topo_hi: the reward stage needs the species count)
+                    lane_park<MM>(L);   // (mixed mode keeps `pres`: the reward stage needs the species count)
                 }
             }
         }
     }
+    if (A.warp_iters && lane == 0) atomicAdd(A.warp_iters, n_iters);
 }
 
 // Stand-alone reward kernel for the test hook: one warp per series.

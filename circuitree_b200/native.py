@@ -109,6 +109,7 @@ class NativeTree:
         self._engine_args = dict(device=device, sim_config=sim_config,
                                  seed=int(self.seed if reward_seed is None else reward_seed) & _MASK64)
         self._strings: dict[int, str] = {}
+        self.timing = {"select_s": 0.0, "submit_s": 0.0, "reward_s": 0.0, "backprop_s": 0.0}
 
     def __del__(self):
         try:
@@ -219,54 +220,98 @@ class NativeTree:
             off += ln
         return out
 
-    def _rewards(self, keys: np.ndarray, handles: np.ndarray) -> np.ndarray:
+    def _submit(self, keys: np.ndarray, handles: np.ndarray) -> dict:
+        """Start the reward batch of a set of selected leaves (asynchronous on the GPU path)."""
         if self.reward_fn is not None:
-            return np.asarray(self.reward_fn([self.key_to_string(int(k)) for k in keys]), dtype=np.float64)
+            return {"rewards": np.asarray(self.reward_fn([self.key_to_string(int(k)) for k in keys]), dtype=np.float64)}
         eng = self.reward_engine
         # group leaves by topology: one job per distinct simulated state ...
         uniq, inverse, counts = np.unique(handles, return_inverse=True, return_counts=True)
-        # ... launched longest-expected-first (events per trajectory seen so far for that topology;
-        # unseen topologies first), which shortens the tail of a launch with few trajectories per lane
+        # ... with the events per trajectory seen so far for that topology as the cost hint of the
+        # longest-first launch order (unseen topologies: assume expensive)
         cost = np.array([eng.cost.get(int(h), np.inf) for h in uniq])
-        order = np.argsort(-cost, kind="stable")
-        rank_of = np.empty_like(order)
-        rank_of[order] = np.arange(len(order))
+        known = cost[np.isfinite(cost)]
+        job_cost = np.where(np.isfinite(cost), cost, float(known.max()) if len(known) else 1.0e6)
         B = self.trajectories_per_reward
-        n_traj = (counts[order] * B).astype(np.uint32)
+        n_traj = (counts * B).astype(np.uint32)
         offsets = np.concatenate(([0], np.cumsum(n_traj, dtype=np.uint64)[:-1])).astype(np.uint64)
         bases = offsets + np.uint64(eng.next_traj)
         eng.next_traj += int(n_traj.sum())
-        out = eng.engine.rewards_host(uniq[order], n_traj, bases, eng.cfg, eng.seed, per_trajectory=True)
-        eng.total_events += int(out["job_events"].sum())
-        eng.total_trajectories += int(n_traj.sum())
-        for h, ev, nt in zip(uniq[order], out["job_events"], n_traj):
-            eng.cost[int(h)] = float(ev) / float(nt)
-        # leaf x of topology u gets the mean of its own block of trajectories_per_reward trajectories
-        per = out["reward"].astype(np.float64)
-        block_means = per.reshape(-1, B).mean(axis=1)
-        first_block = (offsets // np.uint64(B)).astype(np.int64)
-        rewards = np.zeros(len(keys), dtype=np.float64)
-        taken = np.zeros(len(uniq), dtype=np.int64)
-        for x, u in enumerate(inverse):
-            j = rank_of[u]
-            rewards[x] = block_means[first_block[j] + taken[u]]
-            taken[u] += 1
-        return rewards
+        ticket = eng.engine.submit(uniq, n_traj, bases, eng.cfg, eng.seed, job_cost=job_cost)
+        return {"ticket": ticket, "uniq": uniq, "inverse": inverse, "n_traj": n_traj, "offsets": offsets, "n_leaves": len(keys)}
 
-    def search_mcts(self, n_steps: int, batch_size: int = 1, callback: Optional[Callable] = None) -> None:
+    def _collect(self, job: dict) -> np.ndarray:
+        """Wait for a reward batch; leaf x of topology u gets the mean of its own block of
+        ``trajectories_per_reward`` trajectories."""
+        if "rewards" in job:
+            return job["rewards"]
+        eng = self.reward_engine
+        out = eng.engine.wait(job["ticket"], per_trajectory=True)
+        eng.total_events += int(out["job_events"].sum())
+        eng.total_trajectories += int(job["n_traj"].sum())
+        for h, ev, nt in zip(job["uniq"], out["job_events"], job["n_traj"]):
+            eng.cost[int(h)] = float(ev) / float(nt)
+        B = self.trajectories_per_reward
+        block_means = out["reward"].astype(np.float64).reshape(-1, B).mean(axis=1)
+        first_block = (job["offsets"] // np.uint64(B)).astype(np.int64)
+        inverse = job["inverse"]
+        # rank of each leaf among the leaves that share its topology, in selection order
+        order = np.argsort(inverse, kind="stable")
+        rank = np.empty(len(inverse), dtype=np.int64)
+        starts = np.concatenate(([0], np.cumsum(np.bincount(inverse, minlength=len(job["uniq"])))[:-1]))
+        rank[order] = np.arange(len(inverse)) - starts[inverse[order]]
+        return block_means[first_block[inverse] + rank]
+
+    def _rewards(self, keys: np.ndarray, handles: np.ndarray) -> np.ndarray:
+        return self._collect(self._submit(keys, handles))
+
+    def search_mcts(self, n_steps: int, batch_size: int = 1, callback: Optional[Callable] = None,
+                    pipeline_depth: int = 1) -> None:
         """``n_steps`` iterations with ``batch_size`` leaves per reward launch; ``batch_size=1``
-        is the reference's sequential search (circuitree.py:693-771)."""
-        step = 0
-        while step < n_steps:
-            k = min(batch_size, n_steps - step)
-            keys, handles = self.select(k)
-            paths = self.pending_paths() if callback is not None else None
-            rewards = self._rewards(keys, handles)
+        is the reference's sequential search (circuitree.py:693-771).
+
+        ``pipeline_depth > 1`` keeps that many reward batches in flight: the leaves of the next
+        batch are selected -- with the visits of all in-flight leaves already counted, i.e. under
+        virtual loss exactly as in the reference's parallel mode (circuitree.py:532-535) -- while
+        earlier batches are still simulating, so their kernels overlap on the GPU.  Rewards are
+        back-propagated in selection order.
+        """
+        import time
+        from collections import deque
+
+        inflight: deque = deque()
+        step = 0        # leaves selected
+        done = 0        # leaves back-propagated
+
+        def retire():
+            nonlocal done
+            k, keys, paths, job = inflight.popleft()
+            t0 = time.perf_counter()
+            rewards = self._collect(job)
+            t1 = time.perf_counter()
             self.backprop(rewards)
+            self.timing["reward_s"] += t1 - t0
+            self.timing["backprop_s"] += time.perf_counter() - t1
             if callback is not None:
                 for x in range(k):
-                    callback(self, step + x, paths[x], self.key_to_string(int(keys[x])), float(rewards[x]))
+                    callback(self, done + x, paths[x], self.key_to_string(int(keys[x])), float(rewards[x]))
+            done += k
+
+        while step < n_steps:
+            k = min(batch_size, n_steps - step)
+            t0 = time.perf_counter()
+            keys, handles = self.select(k)
+            t1 = time.perf_counter()
+            paths = self.pending_paths()[-k:] if callback is not None else None
+            job = self._submit(keys, handles)
+            self.timing["select_s"] += t1 - t0
+            self.timing["submit_s"] += time.perf_counter() - t1
+            inflight.append((k, keys, paths, job))
             step += k
+            while len(inflight) >= max(1, pipeline_depth):
+                retire()
+        while inflight:
+            retire()
 
     def grow_tree(self) -> None:
         _check(_lib().ct_tree_grow(self._h))

@@ -72,12 +72,13 @@ class RootParallelSearch:
         device: torch device for the collective buffers (``cuda:<local_rank>`` with NCCL, None with gloo).
     """
 
-    def __init__(self, tree, sync_every: int, batch_size: int, device=None):
+    def __init__(self, tree, sync_every: int, batch_size: int, device=None, pipeline_depth: int = 1):
         import torch.distributed as dist
 
         self.tree = tree
         self.sync_every = int(sync_every)
         self.batch_size = int(batch_size)
+        self.pipeline_depth = int(pipeline_depth)
         self.device = device
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
@@ -99,6 +100,6 @@ class RootParallelSearch:
         done = 0
         while done < n_steps_per_rank:
             k = min(self.sync_every, n_steps_per_rank - done)
-            self.tree.search_mcts(k, batch_size=self.batch_size)
+            self.tree.search_mcts(k, batch_size=self.batch_size, pipeline_depth=self.pipeline_depth)
             done += k
             self.sync()

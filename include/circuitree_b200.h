@@ -40,6 +40,8 @@ typedef struct ct_sim_config {
     float init_mean;         /* Poisson mean of initial protein counts, default 10 */
     int32_t schedule;        /* 0 auto; 1 one topology per warp (big jobs); 2 mixed topologies per warp
                                 (many small jobs).  Results are identical, only the speed differs. */
+    int32_t lpt;             /* 1 (default): start trajectories longest-expected-first (cost pre-pass +
+                                radix sort); 0: in id order.  Results are identical. */
     float ranges[CT_N_PARAMS][3]; /* (lo, hi, is_log) per parameter, SPEC.md section 4 */
 } ct_sim_config;
 
@@ -75,11 +77,14 @@ int ct_compile_topology(int32_t n_species, const int64_t *act, int32_t n_act,
  *   d_reward  float32 [total]     d_lag  int32 [total] (nullable)   d_events uint32 [total] (nullable)
  *   d_series  (nullable, debug) uint8 [total][n_species_max][nt/decim] companded block sums
  * `stream` is a cudaStream_t (0 = default stream).  Asynchronous.
+ * job_cost (host, nullable) float32 [n_jobs]: relative expected events per trajectory of each job's
+ * topology (e.g. observed earlier); only steers the longest-first launch order, never the results.
  */
 int ct_launch_rewards(ct_engine *eng, const uint64_t *handles, const uint32_t *n_traj,
-                      const uint64_t *traj_base, int32_t n_jobs, const ct_sim_config *cfg,
-                      uint64_t seed, void *stream, const float *d_params, float *d_reward,
-                      int32_t *d_lag, uint32_t *d_events, uint8_t *d_series, int32_t series_stride);
+                      const uint64_t *traj_base, const float *job_cost, int32_t n_jobs,
+                      const ct_sim_config *cfg, uint64_t seed, void *stream, const float *d_params,
+                      float *d_reward, int32_t *d_lag, uint32_t *d_events, uint8_t *d_series,
+                      int32_t series_stride);
 
 /*
  * Per-job reduction on the device (deterministic order): mean reward (float64), number of
@@ -96,9 +101,22 @@ int ct_reduce_jobs(ct_engine *eng, const uint32_t *n_traj, int32_t n_jobs, void 
  * back.  Synchronous.
  */
 int ct_rewards_host(ct_engine *eng, const uint64_t *handles, const uint32_t *n_traj,
-                    const uint64_t *traj_base, int32_t n_jobs, const ct_sim_config *cfg,
-                    uint64_t seed, const float *h_params, double *h_job_mean,
+                    const uint64_t *traj_base, const float *job_cost, int32_t n_jobs,
+                    const ct_sim_config *cfg, uint64_t seed, const float *h_params, double *h_job_mean,
                     uint64_t *h_job_events, float *h_reward, int32_t *h_lag);
+
+/*
+ * Asynchronous form of ct_rewards_host: submit returns a ticket at once (the batch runs on a
+ * stream of its own, so consecutive batches overlap on the GPU); wait blocks, copies the results
+ * into host buffers (each nullable) and releases the ticket.  Used by the pipelined MCTS
+ * scheduler: leaves of batch k+1 are selected (under virtual loss, reference circuitree.py:532-535)
+ * while batch k is still simulating.
+ */
+int ct_rewards_submit(ct_engine *eng, const uint64_t *handles, const uint32_t *n_traj,
+                      const uint64_t *traj_base, const float *job_cost, int32_t n_jobs,
+                      const ct_sim_config *cfg, uint64_t seed, const float *h_params, int64_t *ticket);
+int ct_rewards_wait(ct_engine *eng, int64_t ticket, double *h_job_mean, uint64_t *h_job_events,
+                    float *h_reward, int32_t *h_lag);
 
 /* Test hook: reward and lag of companded series uint8 [n][n_species][n_dec] (host buffers). */
 int ct_reward_from_series_host(ct_engine *eng, const uint8_t *h_series, int32_t n, int32_t n_species,
@@ -106,6 +124,9 @@ int ct_reward_from_series_host(ct_engine *eng, const uint8_t *h_series, int32_t 
 
 /* Kernel launches issued by this engine since creation (bench.py's gpu_launches). */
 int64_t ct_engine_launch_count(ct_engine *eng);
+/* Debug counter: hot-loop iterations (2 lock-step SSA steps x 32 lanes) of all warps since the last
+ * call (first call enables it); lane utilisation = events / (64 * iterations). */
+int64_t ct_engine_warp_iterations(ct_engine *eng);
 
 /* ---------------------------------------------------------------------------------------------
  * Native host side of the batched MCTS scheduler (csrc/native_tree.cpp): bit-packed

@@ -51,7 +51,7 @@ def handle_of(state):
     return _capi.compile_topology(len(comps), act, inh)
 
 
-def gpu_run(eng, states, n, cfg, seed, bases=None, series=False, params=None):
+def gpu_run(eng, states, n, cfg, seed, bases=None, series=False, params=None, job_cost=None):
     handles = [handle_of(s) for s in states]
     counts = [n] * len(states) if np.isscalar(n) else list(n)
     if bases is None:
@@ -66,7 +66,7 @@ def gpu_run(eng, states, n, cfg, seed, bases=None, series=False, params=None):
     d_params = torch.as_tensor(np.asarray(params, dtype=np.float32), device="cuda") if params is not None else None
     eng.launch_rewards(handles, counts, bases, cfg, seed, 0, d_reward.data_ptr(), d_lag=d_lag.data_ptr(),
                        d_events=d_events.data_ptr(), d_params=d_params.data_ptr() if d_params is not None else 0,
-                       d_series=d_series.data_ptr() if series else 0, series_stride=stride)
+                       d_series=d_series.data_ptr() if series else 0, series_stride=stride, job_cost=job_cost)
     torch.cuda.synchronize()
     out = {"reward": d_reward.cpu().numpy(), "lag": d_lag.cpu().numpy(), "events": d_events.cpu().numpy().astype(np.int64)}
     if series:
@@ -205,6 +205,15 @@ def test_schedules_give_identical_results(eng):
     for k in ("reward", "lag", "events"):
         assert np.array_equal(outs[0][k], outs[1][k]), k
         assert np.array_equal(outs[0][k], outs[2][k]), k
+    # longest-first ordering (and any cost hint) changes the launch order only
+    for schedule in (1, 2):
+        c = small_cfg(nt=320, decim=16)
+        c.schedule, c.lpt = schedule, 0
+        plain = gpu_run(eng, states, counts, c, seed=13, bases=bases)
+        c.lpt = 1
+        hinted = gpu_run(eng, states, counts, c, seed=13, bases=bases, job_cost=rg.random(150) * 100)
+        for k in ("reward", "lag", "events"):
+            assert np.array_equal(plain[k], outs[0][k]) and np.array_equal(hinted[k], outs[0][k]), (schedule, k)
     bad = _capi.default_config(); bad.schedule = 7
     with pytest.raises(_capi.EngineError):
         eng.rewards_host([handle_of("*AB::ABi")], [4], [0], bad, 1)
@@ -252,6 +261,42 @@ def test_get_reward_through_circuitree_api():
     assert tree.graph.nodes["ABC::"]["visits"] == 296
     assert 0.0 < tree.graph.nodes["ABC::"]["reward"] / 296 < 1.0
     assert tree.reward_engine.total_trajectories == (1 + 1 + 3 + 40 + 256) * 256
+
+
+def test_async_submit_wait_matches_sync(eng):
+    c = small_cfg(nt=320, decim=16)
+    hs = [handle_of(s) for s in ["*ABC::ABi_BCi_CAi", "*AB::ABa_BAi", "*ABC::ABa_BCi_CAa"]]
+    t1 = eng.submit(hs, [300, 200, 100], [0, 1000, 2000], c, 5)
+    t2 = eng.submit(hs[:2], [64, 64], [5000, 6000], c, 5)          # two batches in flight
+    b = eng.wait(t2, per_trajectory=True)
+    a = eng.wait(t1, per_trajectory=True)
+    sa = eng.rewards_host(hs, [300, 200, 100], [0, 1000, 2000], c, 5, per_trajectory=True)
+    sb = eng.rewards_host(hs[:2], [64, 64], [5000, 6000], c, 5, per_trajectory=True)
+    for x, y in ((a, sa), (b, sb)):
+        assert np.array_equal(x["reward"], y["reward"]) and np.array_equal(x["lag"], y["lag"])
+        assert np.array_equal(x["job_events"], y["job_events"]) and np.array_equal(x["job_mean"], y["job_mean"])
+    with pytest.raises(_capi.EngineError):
+        eng.wait(t1)                                                # tickets are single-use
+
+
+def test_native_tree_pipelined_gpu_search():
+    from circuitree_b200.native import NativeTree
+
+    def run(depth):
+        t = NativeTree(SimpleNetworkGrammar(list("ABC"), AI, root="ABC::"), "ABC::", seed=3, n_exhausted=np.inf,
+                       trajectories_per_reward=8)
+        t.search_mcts(512, batch_size=64, pipeline_depth=depth)
+        g = t.to_networkx()
+        return g, t
+
+    g, t = run(3)
+    assert g.nodes["ABC::"]["visits"] == 512
+    assert t.reward_engine.total_trajectories == 512 * 8
+    mean = g.nodes["ABC::"]["reward"] / 512
+    assert 0.1 < mean < 0.5
+    g2, _ = run(3)
+    assert sorted((n, d["visits"], d["reward"]) for n, d in g.nodes(data=True)) == \
+        sorted((n, d["visits"], d["reward"]) for n, d in g2.nodes(data=True))
 
 
 def test_same_seed_same_search():
