@@ -180,30 +180,22 @@ __device__ __forceinline__ float compand_block(float s)
     return fminf(floorf(sqrtf(s) + 0.5f), 255.0f);
 }
 
-#ifndef CT_EDGE_BRANCH
-#define CT_EDGE_BRANCH 1     // 1: absent edges are skipped by (warp-uniform) branches; 0: compiler's choice
-#endif
-#ifndef CT_GENE_CHAINS
-#define CT_GENE_CHAINS 0     // 1: one running sum per gene (shorter chains, measured 6 % slower); 0: one global chain
-#endif
-#if CT_EDGE_BRANCH
-#define CT_KEEP_BRANCH() asm volatile("")
-#else
-#define CT_KEEP_BRANCH()
-#endif
-
 // One SSA step (SPEC.md section 2) executed by ALL lanes of the warp in lock-step; lanes without a
 // trajectory carry zero rates (a0 = 0: nothing fires, nothing is recorded), which keeps the hot
-// loop convergent so the topology tests below are warp-uniform branches in uniform mode.
-// `pres` has bit c = i*5+j set when edge i->j exists, `actm` when it activates; species count nsp.
-// Returns false for a lane that has just recorded its last grid sample.
+// loop convergent.  `pres` has bit c = i*5+j set when edge i->j exists, `actm` when it activates;
+// species count nsp.  Returns false for a lane that has just recorded its last grid sample.
 //
-// Selection: s_r = [t < c_r] is monotone along a running sum, so reaction r fires iff
+// Reaction order (SPEC.md section 2), per gene j: transcription, mRNA decay, translation, protein
+// decay, binding of regulator 0..M-1, unbinding of regulator 0..M-1.  The common path treats
+// "some regulator binds at j" (propensity kfree_j * sum_i P_i) and "some regulator unbinds at j"
+// (koff_j * n_j) as two lumped reactions, so it costs 6 running-sum entries per gene whatever the
+// topology; which regulator it is gets resolved from the position of the target inside the lump,
+// in a block that only runs when some lane of the warp fired a (un)binding at that gene.  This is
+// the same direct method: the flat reaction is the one whose running sum first exceeds the target.
+//
+// Selection: s_r = [target < c_r] is monotone along the running sum, so reaction r fires iff
 // s_r - s_{r-1} = 1 and the state updates are differences of neighbouring s values; a reaction with
-// zero propensity has c_r = c_{r-1} and can never fire.  With CT_GENE_CHAINS every gene has its own
-// running sum lc (from 0) and compares t_j = target - (sum of the previous genes' totals) against
-// it; float rounding at a gene boundary can at worst make the step fire no reaction or one
-// reaction in each of two neighbouring genes (probability ~1e-7 per step), never an impossible one.
+// zero propensity has c_r = c_{r-1} and can never fire.
 template <int MM>
 __device__ __forceinline__ bool ssa_step(Lane<MM>& L, const bool active, const uint32_t pres, const uint32_t actm,
                                          const int nsp, uint32_t w_tau, uint32_t w_sel, uint8_t* ser, const int nt,
@@ -211,41 +203,39 @@ __device__ __forceinline__ bool ssa_step(Lane<MM>& L, const bool active, const u
 {
     auto has = [&](int i, int j) -> bool { return (pres >> (i * kTopoStride + j)) & 1u; };
     auto is_act = [&](int i, int j) -> bool { return (actm >> (i * kTopoStride + j)) & 1u; };
-    // ---- propensities as running sums in SPEC order ----
-    float cum[4 * MM + 2 * MM * MM];
-    float off[MM + 1];
+    // ---- propensities as one running sum ----
+    float cum[6 * MM], S[MM], kfree[MM], koff[MM];
     float c = 0.0f;
-    off[0] = 0.0f;
 #pragma unroll
     for (int j = 0; j < MM; ++j) {
-        if (CT_GENE_CHAINS) c = 0.0f;
+        S[j] = 0.0f; kfree[j] = 0.0f; koff[j] = 0.0f;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) cum[6 * j + r] = c;
         if (j < nsp) {
             const float n = L.n[j], na = L.A[j];
             const float km_a = (na > 0.0f) ? L.km1 : L.km0;
             const float km_i = (na > 0.0f) ? L.km3 : L.km2;
-            c += (n > na) ? km_i : km_a;     cum[4 * j + 0] = c;
-            c = fmaf(L.gm, L.R[j], c);       cum[4 * j + 1] = c;
-            c = fmaf(L.kp, L.R[j], c);       cum[4 * j + 2] = c;
-            c = fmaf(L.gp, L.P[j], c);       cum[4 * j + 3] = c;
-            const float koff = (n >= 2.0f) ? L.k_off2 : L.k_off1;
-            const float kfree = L.k_on * (2.0f - n);
+            c += (n > na) ? km_i : km_a;     cum[6 * j + 0] = c;
+            c = fmaf(L.gm, L.R[j], c);       cum[6 * j + 1] = c;
+            c = fmaf(L.kp, L.R[j], c);       cum[6 * j + 2] = c;
+            c = fmaf(L.gp, L.P[j], c);       cum[6 * j + 3] = c;
+            float sp = 0.0f;
 #pragma unroll
-            for (int i = 0; i < MM; ++i) {
-                if (has(i, j)) {
-                    CT_KEEP_BRANCH();
-                    const int r = 4 * MM + 2 * (j * MM + i);
-                    c = fmaf(kfree, L.P[i], c);     cum[r] = c;
-                    c = fmaf(koff, L.b[i][j], c);   cum[r + 1] = c;
-                }
-            }
+            for (int i = 0; i < MM; ++i)
+                if (has(i, j)) sp += L.P[i];
+            S[j] = sp;
+            koff[j] = (n >= 2.0f) ? L.k_off2 : L.k_off1;
+            kfree[j] = L.k_on * (2.0f - n);
+            c = fmaf(kfree[j], sp, c);       cum[6 * j + 4] = c;
+            c = fmaf(koff[j], n, c);         cum[6 * j + 5] = c;
         }
-        if (CT_GENE_CHAINS) off[j + 1] = off[j] + c;
     }
-    const float a0 = CT_GENE_CHAINS ? off[MM] : c;
+    const float a0 = c;
 
     // ---- time to next event; grid samples crossed keep the pre-event state ----
     const float tau = (-0.69314718056f * fast_log2(u01(w_tau))) * fast_rcp(a0);   // a0 == 0 -> +inf
     L.t_rem -= tau;
+    bool alive = true;     // no early return: every lane must reach the warp votes below
     if (active && L.t_rem < 0.0f) {
         do {
 #pragma unroll
@@ -262,43 +252,55 @@ __device__ __forceinline__ bool ssa_step(Lane<MM>& L, const bool active, const u
             }
             L.t_rem += dt;
         } while (L.t_rem < 0.0f && L.k < nt);
-        if (L.k >= nt) return false;
+        alive = L.k < nt;
     }
 
-    // ---- select and fire ----
-    const float target = u01(w_sel) * a0;
+    // ---- select and fire (a lane that has just finished fires nothing: target beyond every sum) ----
+    const float target = alive ? u01(w_sel) * a0 : 3.0e38f;
     float s_prev = 0.0f;
 #pragma unroll
     for (int j = 0; j < MM; ++j) {
+        float d = 0.0f, d_b = 0.0f;
         if (j < nsp) {
-            const float t = CT_GENE_CHAINS ? target - off[j] : target;
-            if (CT_GENE_CHAINS) s_prev = (t < 0.0f) ? 1.0f : 0.0f;
-            const float s_tx = (t < cum[4 * j + 0]) ? 1.0f : 0.0f;
-            const float s_rm = (t < cum[4 * j + 1]) ? 1.0f : 0.0f;
-            const float s_tl = (t < cum[4 * j + 2]) ? 1.0f : 0.0f;
-            const float s_dp = (t < cum[4 * j + 3]) ? 1.0f : 0.0f;
+            const float s_tx = (target < cum[6 * j + 0]) ? 1.0f : 0.0f;
+            const float s_rm = (target < cum[6 * j + 1]) ? 1.0f : 0.0f;
+            const float s_tl = (target < cum[6 * j + 2]) ? 1.0f : 0.0f;
+            const float s_dp = (target < cum[6 * j + 3]) ? 1.0f : 0.0f;
+            const float s_b = (target < cum[6 * j + 4]) ? 1.0f : 0.0f;
+            const float s_u = (target < cum[6 * j + 5]) ? 1.0f : 0.0f;
             L.R[j] += fmaf(2.0f, s_tx, -s_prev) - s_rm;
             L.P[j] += fmaf(2.0f, s_tl, -s_rm) - s_dp;
-            s_prev = s_dp;
+            d_b = s_b - s_dp;                        // 1 if some regulator binds at j
+            d = fmaf(2.0f, s_b, -s_dp) - s_u;        // +1 bind, -1 unbind, 0 neither
+            s_prev = s_u;
+        }
+        // Resolve which regulator (un)binds.  Warp-uniform vote: the hot loop is convergent here.
+        if (__any_sync(kFull, d != 0.0f)) {
+            const bool bind = d_b != 0.0f;
+            const float base = bind ? cum[6 * j + 3] : cum[6 * j + 4];
+            const float scale = bind ? kfree[j] : koff[j];
+            const float tot = bind ? S[j] : L.n[j];                  // molecules in the lump (>= 1 if it fired)
+            float y = (target - base) * fast_rcp(scale);             // position inside the lump, in molecules
+            y = fminf(y, __uint_as_float(__float_as_uint(tot) - 1u)); // strictly below the total: one regulator fires
+            if (d == 0.0f) y = 3.0e38f;                              // lanes that fired nothing here
+            float acc = 0.0f, sq = 0.0f;
 #pragma unroll
             for (int i = 0; i < MM; ++i) {
                 if (has(i, j)) {
-                    CT_KEEP_BRANCH();
-                    const int r = 4 * MM + 2 * (j * MM + i);
-                    const float s_b = (t < cum[r]) ? 1.0f : 0.0f;
-                    const float s_u = (t < cum[r + 1]) ? 1.0f : 0.0f;
-                    const float d = fmaf(2.0f, s_b, -s_prev) - s_u;   // +1 bind, -1 unbind
-                    L.b[i][j] += d;
-                    L.P[i] -= d;
-                    L.n[j] += d;
-                    if (is_act(i, j)) L.A[j] += d;
-                    s_prev = s_u;
+                    acc += bind ? L.P[i] : L.b[i][j];
+                    const float s = (y < acc) ? 1.0f : 0.0f;
+                    const float dd = (s - sq) * d;                   // +-1 for the chosen regulator
+                    sq = s;
+                    L.b[i][j] += dd;
+                    L.P[i] -= dd;
+                    if (is_act(i, j)) L.A[j] += dd;
                 }
             }
+            L.n[j] += d;
         }
     }
-    L.events += active ? 1u : 0u;
-    return true;
+    L.events += (active && alive) ? 1u : 0u;
+    return alive;
 }
 
 // A lane without a trajectory: zero rates and state so that ssa_step is a no-op for it.

@@ -185,7 +185,7 @@ static uint64_t simulate_pairwise(const uint8_t etype[CT_MAX_SPECIES][CT_MAX_SPE
 
     for (;;) {
         /* propensities, SPEC.md §2 order: per target gene j:
-         * tx, mRNA decay, translation, protein decay, then (bind, unbind) per regulator i */
+         * tx, mRNA decay, translation, protein decay, binding of each regulator i, unbinding of each i */
         int nr = 0; double a0 = 0.0;
         for (int j = 0; j < M; ++j) {
             int n = 0, na = 0, nrp = 0;
@@ -199,11 +199,10 @@ static uint64_t simulate_pairwise(const uint8_t etype[CT_MAX_SPECIES][CT_MAX_SPE
             a[nr++] = kp * R[j];
             a[nr++] = gp * P[j];
             double koff = (n >= 2) ? k_off2 : k_off1;
-            for (int i = 0; i < M; ++i) {
-                if (!etype[i][j]) continue;
-                a[nr++] = k_on * P[i] * (double)(2 - n);
-                a[nr++] = koff * (double)b[i][j];
-            }
+            for (int i = 0; i < M; ++i)
+                if (etype[i][j]) a[nr++] = k_on * P[i] * (double)(2 - n);
+            for (int i = 0; i < M; ++i)
+                if (etype[i][j]) a[nr++] = koff * (double)b[i][j];
         }
         for (int r = 0; r < nr; ++r) a0 += a[r];
 
@@ -227,7 +226,7 @@ static uint64_t simulate_pairwise(const uint8_t etype[CT_MAX_SPECIES][CT_MAX_SPE
 
         /* select: first reaction r with target < cumulative sum */
         double target = u2 * a0, c = 0.0;
-        int sel = nr - 1;
+        int sel = -1;   /* rounding can leave none: the step then fires nothing (SPEC.md section 2) */
         for (int r = 0; r < nr; ++r) { c += a[r]; if (target < c) { sel = r; break; } }
 
         /* apply */
@@ -237,11 +236,10 @@ static uint64_t simulate_pairwise(const uint8_t etype[CT_MAX_SPECIES][CT_MAX_SPE
             if (sel == nr++) { R[j] -= 1.0; sel = -1; break; }
             if (sel == nr++) { P[j] += 1.0; sel = -1; break; }
             if (sel == nr++) { P[j] -= 1.0; sel = -1; break; }
-            for (int i = 0; i < M; ++i) {
-                if (!etype[i][j]) continue;
-                if (sel == nr++) { P[i] -= 1.0; b[i][j] += 1; sel = -1; break; }
-                if (sel == nr++) { P[i] += 1.0; b[i][j] -= 1; sel = -1; break; }
-            }
+            for (int i = 0; i < M && sel >= 0; ++i)
+                if (etype[i][j] && sel == nr++) { P[i] -= 1.0; b[i][j] += 1; sel = -1; }
+            for (int i = 0; i < M && sel >= 0; ++i)
+                if (etype[i][j] && sel == nr++) { P[i] += 1.0; b[i][j] -= 1; sel = -1; }
         }
         ++n_events;
     }
