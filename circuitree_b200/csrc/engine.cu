@@ -60,22 +60,21 @@ struct ct_engine {
     int64_t next_ticket = 1;
     int n_sm = 0;
     cudaStream_t stream = nullptr;   // used by the host-buffer entry points
-    KernelInfo k3, k4, k5;          // uniform-topology warps
-    KernelInfo m3, m4, m5;          // mixed-topology warps
+    KernelInfo ki[3][2][2];         // [M-3][mixed][all jobs have M species]
     int64_t launches = 0;
     unsigned long long* d_warp_iters = nullptr;   // debug counter (ct_engine_warp_iterations)
 };
 
 namespace {
 
-template <int MM, bool kMixed>
+template <int MM, bool kMixed, bool kAll>
 int prepare_kernel(KernelInfo& ki)
 {
     ki.smem = (size_t)ct::kThreads * MM * ct::kSerStride + (ct::kThreads / 32) * ct::kSerStride * sizeof(float);
-    CT_CUDA(cudaFuncSetAttribute(ct::ssa_pairwise_kernel<MM, kMixed>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
-    CT_CUDA(cudaFuncSetAttribute(ct::ssa_pairwise_kernel<MM, kMixed>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    CT_CUDA(cudaFuncSetAttribute(ct::ssa_pairwise_kernel<MM, kMixed, kAll>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
+    CT_CUDA(cudaFuncSetAttribute(ct::ssa_pairwise_kernel<MM, kMixed, kAll>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared));
-    CT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.blocks_per_sm, ct::ssa_pairwise_kernel<MM, kMixed>, ct::kThreads,
+    CT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.blocks_per_sm, ct::ssa_pairwise_kernel<MM, kMixed, kAll>, ct::kThreads,
                                                           ki.smem));
     if (ki.blocks_per_sm < 1) return fail(CT_ERR_CUDA, "SSA kernel (M=%d) does not fit on an SM", MM);
     return CT_OK;
@@ -137,12 +136,12 @@ int ct_engine_create(int device, ct_engine** out)
     eng->n_sm = prop.multiProcessorCount;
     CT_CUDA(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
     int rc;
-    if ((rc = prepare_kernel<3, false>(eng->k3)) != CT_OK) { delete eng; return rc; }
-    if ((rc = prepare_kernel<4, false>(eng->k4)) != CT_OK) { delete eng; return rc; }
-    if ((rc = prepare_kernel<5, false>(eng->k5)) != CT_OK) { delete eng; return rc; }
-    if ((rc = prepare_kernel<3, true>(eng->m3)) != CT_OK) { delete eng; return rc; }
-    if ((rc = prepare_kernel<4, true>(eng->m4)) != CT_OK) { delete eng; return rc; }
-    if ((rc = prepare_kernel<5, true>(eng->m5)) != CT_OK) { delete eng; return rc; }
+#define CT_PREP(MM, MIXED, ALL) \
+    if ((rc = prepare_kernel<MM, MIXED, ALL>(eng->ki[MM - 3][MIXED][ALL])) != CT_OK) { delete eng; return rc; }
+    CT_PREP(3, false, false) CT_PREP(3, false, true) CT_PREP(3, true, false) CT_PREP(3, true, true)
+    CT_PREP(4, false, false) CT_PREP(4, false, true) CT_PREP(4, true, false) CT_PREP(4, true, true)
+    CT_PREP(5, false, false) CT_PREP(5, false, true) CT_PREP(5, true, false) CT_PREP(5, true, true)
+#undef CT_PREP
     *out = eng;
     return CT_OK;
 }
@@ -164,7 +163,7 @@ int ct_engine_info(ct_engine* eng, int32_t* n_sm, int32_t* resident_lanes)
 {
     if (!eng) return fail(CT_ERR_INVALID, "engine is NULL");
     if (n_sm) *n_sm = eng->n_sm;
-    if (resident_lanes) *resident_lanes = eng->n_sm * eng->k3.blocks_per_sm * ct::kThreads;
+    if (resident_lanes) *resident_lanes = eng->n_sm * eng->ki[0][0][1].blocks_per_sm * ct::kThreads;
     return CT_OK;
 }
 
@@ -276,6 +275,10 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
     }
     A.seed_lo = (uint32_t)seed;
     A.seed_hi = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        A.rk[2 * r] = A.seed_lo + (uint32_t)r * 0x9E3779B9u;
+        A.rk[2 * r + 1] = A.seed_hi + (uint32_t)r * 0xBB67AE85u;
+    }
     A.total = (uint32_t)total;
     A.order = nullptr;
     A.warp_iters = eng->d_warp_iters;
@@ -317,15 +320,21 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
         eng->launches += 2;
         A.order = d_order;
     }
-    const KernelInfo& ki = mixed ? (max_nsp <= 3 ? eng->m3 : (max_nsp == 4 ? eng->m4 : eng->m5))
-                                 : (max_nsp <= 3 ? eng->k3 : (max_nsp == 4 ? eng->k4 : eng->k5));
+    const int mm = max_nsp <= 3 ? 3 : (int)max_nsp;
+    bool all_full = true;
+    for (int j = 0; j < n_jobs; ++j) all_full = all_full && (ct::topo_nspecies(handles[j]) == (uint32_t)mm || n_traj[j] == 0);
+    const KernelInfo& ki = eng->ki[mm - 3][mixed ? 1 : 0][all_full ? 1 : 0];
     uint64_t want_blocks = (total + ct::kThreads - 1) / ct::kThreads;
     uint64_t max_blocks = (uint64_t)eng->n_sm * ki.blocks_per_sm;
     const unsigned grid = (unsigned)(want_blocks < max_blocks ? want_blocks : max_blocks);
-#define CT_LAUNCH(MM, MIXED) ct::ssa_pairwise_kernel<MM, MIXED><<<grid, ct::kThreads, ki.smem, stream>>>(A)
-    if (max_nsp <= 3) { if (mixed) CT_LAUNCH(3, true); else CT_LAUNCH(3, false); }
-    else if (max_nsp == 4) { if (mixed) CT_LAUNCH(4, true); else CT_LAUNCH(4, false); }
-    else { if (mixed) CT_LAUNCH(5, true); else CT_LAUNCH(5, false); }
+#define CT_LAUNCH(MM, MIXED, ALL) ct::ssa_pairwise_kernel<MM, MIXED, ALL><<<grid, ct::kThreads, ki.smem, stream>>>(A)
+#define CT_LAUNCH_M(MM)                                                          \
+    do {                                                                         \
+        if (mixed) { if (all_full) CT_LAUNCH(MM, true, true); else CT_LAUNCH(MM, true, false); }     \
+        else { if (all_full) CT_LAUNCH(MM, false, true); else CT_LAUNCH(MM, false, false); }         \
+    } while (0)
+    if (mm == 3) CT_LAUNCH_M(3); else if (mm == 4) CT_LAUNCH_M(4); else CT_LAUNCH_M(5);
+#undef CT_LAUNCH_M
 #undef CT_LAUNCH
     CT_CUDA(cudaGetLastError());
     eng->launches += 1;

@@ -49,6 +49,7 @@ struct LaunchArgs {
     float rng_span[10];
     uint32_t log_mask;
     uint32_t seed_lo, seed_hi;
+    uint32_t rk[20];                 // Philox round keys (k0 + r*W0, k1 + r*W1), r = 0..9
     int32_t nt, decim, n_dec;
     float dt, init_mean;
 };
@@ -180,6 +181,20 @@ __device__ __forceinline__ float compand_block(float s)
     return fminf(floorf(sqrtf(s) + 0.5f), 255.0f);
 }
 
+// A lane without a trajectory: zero rates and state so that ssa_step is a no-op for it.
+template <int MM>
+__device__ __forceinline__ void lane_park(Lane<MM>& L)
+{
+    L.k_on = L.k_off1 = L.k_off2 = L.km0 = L.km1 = L.km2 = L.km3 = L.kp = L.gm = L.gp = 0.0f;
+#pragma unroll
+    for (int j = 0; j < MM; ++j) {
+        L.P[j] = L.R[j] = L.blk[j] = L.n[j] = L.A[j] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < MM; ++i) L.b[i][j] = 0.0f;
+    }
+    L.t_rem = 0.0f;
+}
+
 // One SSA step (SPEC.md section 2) executed by ALL lanes of the warp in lock-step; lanes without a
 // trajectory carry zero rates (a0 = 0: nothing fires, nothing is recorded), which keeps the hot
 // loop convergent.  `pres` has bit c = i*5+j set when edge i->j exists, `actm` when it activates;
@@ -196,11 +211,12 @@ __device__ __forceinline__ float compand_block(float s)
 // Selection: s_r = [target < c_r] is monotone along the running sum, so reaction r fires iff
 // s_r - s_{r-1} = 1 and the state updates are differences of neighbouring s values; a reaction with
 // zero propensity has c_r = c_{r-1} and can never fire.
-template <int MM>
-__device__ __forceinline__ bool ssa_step(Lane<MM>& L, const bool active, const uint32_t pres, const uint32_t actm,
-                                         const int nsp, uint32_t w_tau, uint32_t w_sel, uint8_t* ser, const int nt,
-                                         const int decim, const float dt)
+template <int MM, bool kAllSpecies>
+__device__ __forceinline__ void ssa_step(Lane<MM>& L, bool& active, bool& finished, const uint32_t pres,
+                                         const uint32_t actm, const int nsp_in, uint32_t w_tau, uint32_t w_sel,
+                                         uint8_t* ser, const int nt, const int decim, const float dt)
 {
+    const int nsp = kAllSpecies ? MM : nsp_in;   // kAllSpecies: every job has MM species, no per-gene tests
     auto has = [&](int i, int j) -> bool { return (pres >> (i * kTopoStride + j)) & 1u; };
     auto is_act = [&](int i, int j) -> bool { return (actm >> (i * kTopoStride + j)) & 1u; };
     // ---- propensities as one running sum ----
@@ -208,10 +224,7 @@ __device__ __forceinline__ bool ssa_step(Lane<MM>& L, const bool active, const u
     float c = 0.0f;
 #pragma unroll
     for (int j = 0; j < MM; ++j) {
-        S[j] = 0.0f; kfree[j] = 0.0f; koff[j] = 0.0f;
-#pragma unroll
-        for (int r = 0; r < 6; ++r) cum[6 * j + r] = c;
-        if (j < nsp) {
+        if (j < nsp) {   // (entries of absent genes stay unset: pass 2 never consults them)
             const float n = L.n[j], na = L.A[j];
             const float km_a = (na > 0.0f) ? L.km1 : L.km0;
             const float km_i = (na > 0.0f) ? L.km3 : L.km2;
@@ -236,6 +249,7 @@ __device__ __forceinline__ bool ssa_step(Lane<MM>& L, const bool active, const u
     const float tau = (-0.69314718056f * fast_log2(u01(w_tau))) * fast_rcp(a0);   // a0 == 0 -> +inf
     L.t_rem -= tau;
     bool alive = true;     // no early return: every lane must reach the warp votes below
+    const bool was_active = active;
     if (active && L.t_rem < 0.0f) {
         do {
 #pragma unroll
@@ -252,7 +266,11 @@ __device__ __forceinline__ bool ssa_step(Lane<MM>& L, const bool active, const u
             }
             L.t_rem += dt;
         } while (L.t_rem < 0.0f && L.k < nt);
-        alive = L.k < nt;
+        if (L.k >= nt) {           // last grid sample recorded: the lane parks until the warp reduces its record
+            alive = false;
+            active = false;
+            finished = true;
+        }
     }
 
     // ---- select and fire (a lane that has just finished fires nothing: target beyond every sum) ----
@@ -299,22 +317,8 @@ __device__ __forceinline__ bool ssa_step(Lane<MM>& L, const bool active, const u
             L.n[j] += d;
         }
     }
-    L.events += (active && alive) ? 1u : 0u;
-    return alive;
-}
-
-// A lane without a trajectory: zero rates and state so that ssa_step is a no-op for it.
-template <int MM>
-__device__ __forceinline__ void lane_park(Lane<MM>& L)
-{
-    L.k_on = L.k_off1 = L.k_off2 = L.km0 = L.km1 = L.km2 = L.km3 = L.kp = L.gm = L.gp = 0.0f;
-#pragma unroll
-    for (int j = 0; j < MM; ++j) {
-        L.P[j] = L.R[j] = L.blk[j] = L.n[j] = L.A[j] = 0.0f;
-#pragma unroll
-        for (int i = 0; i < MM; ++i) L.b[i][j] = 0.0f;
-    }
-    L.t_rem = 0.0f;
+    L.events += (was_active && alive) ? 1u : 0u;
+    if (!alive) lane_park<MM>(L);   // zero rates and state (rare; after the last use of the state above)
 }
 
 // Parameter vector of one trajectory (SPEC.md sections 3-4): explicit if given, else sampled.
@@ -431,7 +435,7 @@ __device__ __forceinline__ void lane_init(Lane<MM>& L, const LaunchArgs& A, cons
 // topology waits until the warp has drained) -- best for big jobs.  kMixed = true: every lane carries
 // its own topology, tiles are handed out without draining -- best for MCTS batches of many small jobs.
 // Results are identical in both modes.
-template <int MM, bool kMixed>
+template <int MM, bool kMixed, bool kAllSpecies>
 __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa_pairwise_kernel(const LaunchArgs A)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -561,7 +565,7 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa
         ++n_iters;
 
         // two steps per Philox block (SPEC.md section 3); every lane runs them, parked lanes as no-ops
-        const Philox4 x = philox4x32_10(L.ctr, 1u, L.traj_lo, L.traj_hi, A.seed_lo, A.seed_hi);
+        const Philox4 x = philox4x32_10_rk(L.ctr, 1u, L.traj_lo, L.traj_hi, A.rk);
         L.ctr += 1;
         // A warp-wide OR of identical values: the result is warp-uniform by construction, which lets
         // the compiler keep the topology in uniform registers and branch uniformly on its bits.
@@ -569,17 +573,9 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa
         const uint32_t u_act = kMixed ? actm : __reduce_or_sync(kFull, actm);
         const int u_nsp = (int)(u_pres >> 28);
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-            const bool alive = ssa_step<MM>(L, active, u_pres, u_act, u_nsp, h ? x.w[2] : x.w[0],
-                                            h ? x.w[3] : x.w[1], ser, A.nt, A.decim, A.dt);
-            if (__any_sync(kFull, !alive)) {   // rare, warp-uniform: keep the parking code off the hot path
-                if (!alive) {
-                    active = false;
-                    finished = true;
-                    lane_park<MM>(L);   // (mixed mode keeps `pres`: the reward stage needs the species count)
-                }
-            }
-        }
+        for (int h = 0; h < 2; ++h)
+            ssa_step<MM, kAllSpecies>(L, active, finished, u_pres, u_act, u_nsp, h ? x.w[2] : x.w[0], h ? x.w[3] : x.w[1],
+                                      ser, A.nt, A.decim, A.dt);
     }
     if (A.warp_iters && lane == 0) atomicAdd(A.warp_iters, n_iters);
 }
