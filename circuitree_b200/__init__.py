@@ -8,8 +8,8 @@ from . import _capi, _capi_defaults
 from .circuitree import CircuiTree, ExhaustionError, ucb_score
 from .grammar import CircuitGrammar
 from .models import DimersGrammar, SimpleNetworkGrammar
-from .oscillation import OscillationTree, RewardEngine
+from .oscillation import OscillationTree, RewardEngine, reward_landscape
 
 __version__ = "0.1.0"
-__all__ = ["CircuiTree", "CircuitGrammar", "DimersGrammar", "ExhaustionError", "OscillationTree", "RewardEngine",
+__all__ = ["CircuiTree", "CircuitGrammar", "DimersGrammar", "ExhaustionError", "OscillationTree", "RewardEngine", "reward_landscape",
            "SimpleNetworkGrammar", "ucb_score"]

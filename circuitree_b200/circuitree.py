@@ -404,6 +404,15 @@ class CircuiTree(ABC):
     def copy_graph(self) -> nx.DiGraph:
         return self.graph.copy()
 
+    def get_rng_state(self) -> dict:
+        """JSON-serialisable state of ``self.rg`` (the reference does not save it -- ``rg`` is excluded
+        at circuitree.py:129-133 -- so its resumed searches are not reproducible)."""
+        st = self.rg.bit_generator.state
+        return json.loads(json.dumps(st, default=_json_default))
+
+    def set_rng_state(self, state: dict) -> None:
+        self.rg.bit_generator.state = state
+
     def get_attributes(self, attrs_copy: Optional[Iterable[str]]) -> dict:
         """Serialisable attributes; objects with ``to_dict`` are converted (circuitree.py:922-966)."""
         blocked = set(self._non_serializable_attrs)
@@ -431,8 +440,11 @@ class CircuiTree(ABC):
         if json_file is None:
             return gml_target
         json_target = Path(json_file).with_suffix(".json")
+        attrs = self.get_attributes(save_attrs)
+        if save_attrs is None:
+            attrs["rng_state"] = self.get_rng_state()      # extra key; the reference's from_file passes it on as a kwarg
         with json_target.open("w") as f:
-            json.dump(self.get_attributes(save_attrs), f, indent=4, default=_json_default)
+            json.dump(attrs, f, indent=4, default=_json_default)
         return gml_target, json_target
 
     @staticmethod
@@ -468,7 +480,11 @@ class CircuiTree(ABC):
         else:
             graph = nx.parse_gml(graph_gml)
         grammar = cls._generate_grammar(grammar_cls, kwargs.pop("grammar", {}) | (grammar_kwargs or {}))
-        return cls(grammar=grammar, graph=graph, **kwargs)
+        rng_state = kwargs.pop("rng_state", None)
+        tree = cls(grammar=grammar, graph=graph, **kwargs)
+        if rng_state is not None:
+            tree.set_rng_state(rng_state)       # resume is bit-reproducible
+        return tree
 
 
 def _is_file(p) -> bool:

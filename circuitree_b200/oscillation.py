@@ -20,7 +20,7 @@ import numpy as np
 from . import _capi
 from .circuitree import CircuiTree
 
-__all__ = ["OscillationTree", "RewardEngine"]
+__all__ = ["OscillationTree", "RewardEngine", "reward_landscape"]
 
 
 class RewardEngine:
@@ -119,3 +119,28 @@ class OscillationTree(CircuiTree):
     def is_success(self, terminal_state: Hashable) -> bool:
         node = self.graph.nodes[terminal_state]
         return node["visits"] > 0 and node["reward"] / node["visits"] > self.success_threshold
+
+
+def reward_landscape(engine: RewardEngine, states: Sequence[Hashable], n_per_state: int, chunk: int = 1 << 22,
+                     rank: int = 0, world: int = 1) -> dict:
+    """Mean reward, its standard error and the success fraction (reward > 0.4) of every state:
+    the exhaustive "reward landscape" of BASELINE config 5.  States are dealt round-robin to
+    ``world`` ranks (no communication: every (state, trajectory) pair is independent) and simulated
+    in launches of at most ``chunk`` trajectories; trajectory ids are ``state_index * n_per_state + k``
+    so the result does not depend on the sharding."""
+    states = list(states)
+    mine = list(range(rank, len(states), world))
+    out = {"index": np.array(mine, dtype=np.int64), "mean": np.zeros(len(mine)), "sem": np.zeros(len(mine)),
+           "success": np.zeros(len(mine)), "events": np.zeros(len(mine), dtype=np.uint64)}
+    per_launch = max(1, chunk // n_per_state)
+    for a in range(0, len(mine), per_launch):
+        idx = mine[a: a + per_launch]
+        bases = [i * n_per_state for i in idx]
+        res = engine.run([states[i] for i in idx], n_per_state, per_trajectory=True, traj_base=bases)
+        r = res["reward"].reshape(len(idx), n_per_state).astype(np.float64)
+        sl = slice(a, a + len(idx))
+        out["mean"][sl] = r.mean(axis=1)
+        out["sem"][sl] = r.std(axis=1, ddof=1) / np.sqrt(n_per_state) if n_per_state > 1 else 0.0
+        out["success"][sl] = (r > 0.4).mean(axis=1)
+        out["events"][sl] = res["job_events"]
+    return out

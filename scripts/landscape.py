@@ -1,0 +1,38 @@
+"""BASELINE config 5: reward landscape of every 3-component topology (and, sampled, 4-component ones).
+
+    python scripts/landscape.py [--n 10000] [--components 3] [--limit K]
+    torchrun --nproc-per-node 8 scripts/landscape.py --n 10000        # sharded, no collective
+
+Enumerates the terminal states natively (ct_tree_grow), shards them round-robin over ranks and
+simulates n parameter sets per topology on the GPU; prints throughput and the top topologies.
+"""
+import argparse, json, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+from circuitree_b200 import RewardEngine, SimpleNetworkGrammar, reward_landscape
+from circuitree_b200.native import NativeTree
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--n", type=int, default=10000)
+ap.add_argument("--components", type=int, default=3)
+ap.add_argument("--limit", type=int, default=0, help="only the first K terminal states (0 = all)")
+args = ap.parse_args()
+rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+comps = list("ABCDE"[: args.components])
+grammar = SimpleNetworkGrammar(comps, ["activates", "inhibits"], root="".join(comps) + "::")
+tree = NativeTree(grammar, grammar.root, seed=0, reward_fn=lambda s: [0.0] * len(s))
+t0 = time.perf_counter(); tree.grow_tree(); t_enum = time.perf_counter() - t0
+keys = tree.export()["node_keys"]
+terminals = sorted(tree.key_to_string(int(k)) for k in keys if (int(k) >> 62) & 1)
+if args.limit:
+    terminals = terminals[: args.limit]
+eng = RewardEngine(grammar, device=int(os.environ.get("LOCAL_RANK", 0)), seed=0)
+t0 = time.perf_counter()
+res = reward_landscape(eng, terminals, args.n, rank=rank, world=world)
+dt = time.perf_counter() - t0
+best = np.argsort(-res["mean"])[:5]
+print(json.dumps({"rank": rank, "world": world, "terminal_states": len(terminals), "enumeration_s": round(t_enum, 3),
+                  "states_this_rank": len(res["index"]), "trajectories": len(res["index"]) * args.n,
+                  "events": int(res["events"].sum()), "seconds": round(dt, 2),
+                  "reaction_steps_per_s": float(res["events"].sum() / dt),
+                  "top": [[terminals[res["index"][i]], round(float(res["mean"][i]), 4), round(float(res["success"][i]), 3)] for i in best]}))

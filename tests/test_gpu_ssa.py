@@ -299,6 +299,35 @@ def test_native_tree_pipelined_gpu_search():
         sorted((n, d["visits"], d["reward"]) for n, d in g2.nodes(data=True))
 
 
+def test_search_bfs_batched_on_gpu():
+    """search_bfs (reference circuitree.py:601-691) with the GPU reward, visits grouped into launches."""
+    grammar = SimpleNetworkGrammar(list("AB"), AI, root="AB::")
+    tree = OscillationTree(grammar=grammar, root="AB::", seed=2, n_exhausted=np.inf, trajectories_per_reward=4)
+    tree.search_bfs(n_cycles=1, batch_size=256)
+    terminals = [n for n in tree.graph.nodes if n.startswith("*")]
+    assert len(terminals) > 20
+    assert all(tree.graph.nodes[n]["visits"] == 1 for n in terminals)
+    assert all(0.0 <= tree.graph.nodes[n]["reward"] <= 1.0 for n in terminals)
+    assert tree.reward_engine.total_trajectories == 4 * len(terminals)
+
+
+def test_reward_landscape_is_sharding_independent():
+    from circuitree_b200 import reward_landscape
+
+    grammar = SimpleNetworkGrammar(list("ABC"), AI, root="ABC::")
+    states = ["*ABC::ABi_BCi_CAi", "*ABC::ABa_BCa_CAa", "*ABC::AAi", "*ABC::ABi_BAi", "*ABC::ABa_BCi_CAa"]
+    cfg = small_cfg(nt=480, decim=16)
+    whole = reward_landscape(RewardEngine(grammar, device=0, sim_config=cfg, seed=4), states, 128)
+    parts = [reward_landscape(RewardEngine(grammar, device=0, sim_config=cfg, seed=4), states, 128, chunk=256, rank=r, world=2)
+             for r in range(2)]
+    merged = np.zeros(len(states))
+    for p in parts:
+        merged[p["index"]] = p["mean"]
+    assert np.array_equal(merged, whole["mean"])
+    assert whole["mean"][0] > whole["mean"][1]          # repressilator oscillates, the activation ring does not
+    assert (whole["sem"] > 0).all() and (whole["success"] <= 1).all()
+
+
 def test_same_seed_same_search():
     def run():
         grammar = SimpleNetworkGrammar(list("ABC"), AI, root="ABC::")

@@ -161,6 +161,51 @@ def test_file_roundtrip(tmp_path):
         tree.get_attributes(["graph"])
 
 
+def test_resume_from_checkpoint_is_reproducible(tmp_path):
+    """RNG state travels with the checkpoint (the reference drops it, circuitree.py:129-133)."""
+    g = SimpleNetworkGrammar(list("ABC"), AI, root="ABC::")
+    full = CrcTree(grammar=g, root="ABC::", seed=8, n_exhausted=np.inf)
+    full.search_mcts(300)
+    half = CrcTree(grammar=SimpleNetworkGrammar(list("ABC"), AI, root="ABC::"), root="ABC::", seed=8, n_exhausted=np.inf)
+    half.search_mcts(150)
+    gml, js = half.to_file(tmp_path / "half", tmp_path / "half")
+    resumed = CrcTree.from_file(gml, js)
+    resumed.search_mcts(150)
+    assert graph_digest(resumed.graph) == graph_digest(full.graph)
+
+
+def test_reference_can_load_our_checkpoint(tmp_path):
+    """GML + JSON written here load in the unmodified reference (only where it is mounted)."""
+    import importlib.util
+    import sys
+
+    ref_root = "/root/reference"
+    if not importlib.util.find_spec("networkx") or not __import__("os").path.isdir(ref_root):
+        pytest.skip("reference checkout not available on this machine")
+    tree = CrcTree(grammar=SimpleNetworkGrammar(list("ABC"), AI, root="ABC::"), root="ABC::", seed=5, n_exhausted=1e9)
+    tree.search_mcts(120)
+    gml, js = tree.to_file(tmp_path / "t", tmp_path / "t")
+    code = f"""
+import sys, json
+sys.path.insert(0, {ref_root!r})
+import circuitree
+from circuitree.models import SimpleNetworkGrammar
+class T(circuitree.CircuiTree):
+    def get_reward(self, s, **k): return 0.0
+t = T.from_file({str(gml)!r}, {str(js)!r}, grammar_cls=SimpleNetworkGrammar)
+print(json.dumps([t.graph.number_of_nodes(), t.graph.number_of_edges(), t.graph.nodes["ABC::"]["visits"], t.root]))
+"""
+    import subprocess
+
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env={"PYTHONDONTWRITEBYTECODE": "1", "PATH": "/usr/bin:/bin"})
+    assert res.returncode == 0, res.stderr[-1500:]
+    import json
+
+    nn, ne, visits, root = json.loads(res.stdout.strip().splitlines()[-1])
+    assert (nn, ne) == (tree.graph.number_of_nodes(), tree.graph.number_of_edges())
+    assert visits == 120 and root == "ABC::"
+
+
 def test_missing_root_in_supplied_graph():
     import networkx as nx
 
