@@ -11,7 +11,11 @@ from typing import Optional, Sequence
 
 import numpy as np
 
-N_PARAMS = 10
+N_PARAMS = 10          # pairwise model (SPEC.md section 4)
+N_PARAMS_DIMER = 12    # dimer model (SPEC.md section 9)
+MAX_PARAMS = 12
+MAX_INTERACTIONS = 10
+DIMER_TAG = 1 << 63    # set in handles of k = 3 topologies
 MAX_SPECIES = 5
 MAX_NDEC = 126
 
@@ -36,15 +40,19 @@ class SimConfig(ctypes.Structure):
         ("init_mean", ctypes.c_float),
         ("schedule", ctypes.c_int32),
         ("lpt", ctypes.c_int32),
-        ("ranges", (ctypes.c_float * 3) * N_PARAMS),
+        ("ranges", (ctypes.c_float * 3) * MAX_PARAMS),
     ]
 
-    def ranges_array(self) -> np.ndarray:
-        return np.array([[self.ranges[i][j] for j in range(3)] for i in range(N_PARAMS)], dtype=np.float64)
+    def ranges_array(self, n: int = N_PARAMS) -> np.ndarray:
+        """First ``n`` (lo, hi, is_log) rows: 10 for the pairwise model, 12 for the dimer model."""
+        return np.array([[self.ranges[i][j] for j in range(3)] for i in range(n)], dtype=np.float64)
 
     def set_ranges(self, ranges) -> None:
-        r = np.asarray(ranges, dtype=np.float32).reshape(N_PARAMS, 3)
-        for i in range(N_PARAMS):
+        """Overwrite the first ``len(ranges)`` rows (10 or 12)."""
+        r = np.asarray(ranges, dtype=np.float32).reshape(-1, 3)
+        if r.shape[0] > MAX_PARAMS:
+            raise ValueError(f"at most {MAX_PARAMS} parameter ranges")
+        for i in range(r.shape[0]):
             for j in range(3):
                 self.ranges[i][j] = float(r[i, j])
 
@@ -107,8 +115,19 @@ def default_config() -> SimConfig:
     return cfg
 
 
+def is_dimer_handle(handle: int) -> bool:
+    return bool(int(handle) & DIMER_TAG)
+
+
+def _params_array(params, handles, total: int) -> np.ndarray:
+    width = N_PARAMS_DIMER if len(handles) and is_dimer_handle(handles[0]) else N_PARAMS
+    return np.ascontiguousarray(params, dtype=np.float32).reshape(total, width)
+
+
 def compile_topology(n_species: int, activations, inhibitions, k: int = 2) -> int:
-    """``parse_genotype`` arrays (reference models.py:441-480) -> 64-bit topology handle."""
+    """``parse_genotype`` arrays -> 64-bit topology handle: k = 2 rows (regulator, target) of
+    SimpleNetworkGrammar (reference models.py:441-480); k = 3 rows (monomer1, monomer2, target) of
+    DimersGrammar (reference models.py:844-884), ``n_species`` = components + regulators."""
     act = np.ascontiguousarray(np.asarray(activations, dtype=np.int64).reshape(-1, k))
     inh = np.ascontiguousarray(np.asarray(inhibitions, dtype=np.int64).reshape(-1, k))
     h = ctypes.c_uint64(0)
@@ -189,7 +208,7 @@ class Engine:
         reward = np.zeros(total, dtype=np.float32) if per_trajectory else None
         lag = np.zeros(total, dtype=np.int32) if per_trajectory else None
         if params is not None:
-            params = np.ascontiguousarray(params, dtype=np.float32).reshape(total, N_PARAMS)
+            params = _params_array(params, handles, total)
         if job_cost is not None:
             job_cost = np.ascontiguousarray(job_cost, dtype=np.float32)
         check(lib().ct_rewards_host(self._h, handles.ctypes.data, n_traj.ctypes.data, traj_base.ctypes.data, _ptr(job_cost), n_jobs,
@@ -209,7 +228,7 @@ class Engine:
         traj_base = np.ascontiguousarray(traj_base, dtype=np.uint64)
         total = int(n_traj.sum())
         if params is not None:
-            params = np.ascontiguousarray(params, dtype=np.float32).reshape(total, N_PARAMS)
+            params = _params_array(params, handles, total)
         if job_cost is not None:
             job_cost = np.ascontiguousarray(job_cost, dtype=np.float32)
         ticket = ctypes.c_int64(0)

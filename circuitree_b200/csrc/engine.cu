@@ -7,11 +7,14 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <array>
 #include <map>
+#include <mutex>
 #include <vector>
 
 #include "../../include/circuitree_b200.h"
 #include "ssa_pairwise.cuh"
+#include "ssa_dimers.cuh"
 
 namespace {
 
@@ -39,6 +42,19 @@ struct KernelInfo {
     size_t smem = 0;
 };
 
+// Process-wide, append-only table of dimer topologies (SPEC.md section 9); a k = 3 handle is
+// kDimerTag | n_tf << 56 | index into this table.
+constexpr uint64_t kDimerTag = 1ull << 63;
+std::mutex g_dimer_mutex;
+std::vector<ct::DimerTopo> g_dimer_topos;
+std::map<std::array<uint8_t, sizeof(ct::DimerTopo)>, uint32_t> g_dimer_index;
+
+inline bool is_dimer_handle(uint64_t h) { return (h & kDimerTag) != 0; }
+inline int params_per_trajectory(const uint64_t* handles, int n_jobs)
+{
+    return (n_jobs > 0 && is_dimer_handle(handles[0])) ? CT_N_PARAMS_DIMER : CT_N_PARAMS;
+}
+
 }  // namespace
 
 namespace {
@@ -61,6 +77,7 @@ struct ct_engine {
     int n_sm = 0;
     cudaStream_t stream = nullptr;   // used by the host-buffer entry points
     KernelInfo ki[3][2][2];         // [M-3][mixed][all jobs have M species]
+    KernelInfo ki_dimers;
     int64_t launches = 0;
     unsigned long long* d_warp_iters = nullptr;   // debug counter (ct_engine_warp_iterations)
 };
@@ -103,9 +120,10 @@ int ct_version(void) { return 100; }
 int ct_default_config(ct_sim_config* cfg)
 {
     if (!cfg) return fail(CT_ERR_INVALID, "cfg is NULL");
-    static const float r[CT_N_PARAMS][3] = {
+    static const float r[CT_MAX_PARAMS][3] = {
         {-2.3f, -1.7f, 1.f}, {-1.0f, -0.4f, 1.f}, {-2.7f, -2.1f, 1.f}, {-0.3f, 0.3f, 1.f}, {0.0f, 0.6f, 1.f},
-        {-3.5f, -2.5f, 1.f}, {-1.3f, -0.7f, 1.f}, {-1.9f, -1.3f, 1.f}, {-2.0f, -1.4f, 1.f}, {-2.7f, -2.1f, 1.f}};
+        {-3.5f, -2.5f, 1.f}, {-1.3f, -0.7f, 1.f}, {-1.9f, -1.3f, 1.f}, {-2.0f, -1.4f, 1.f}, {-2.7f, -2.1f, 1.f},
+        {-5.3f, -4.7f, 1.f}, {-2.8f, -2.2f, 1.f}};
     cfg->nt = 2000;
     cfg->decim = 16;
     cfg->dt = 20.0f;
@@ -142,6 +160,19 @@ int ct_engine_create(int device, ct_engine** out)
     CT_PREP(4, false, false) CT_PREP(4, false, true) CT_PREP(4, true, false) CT_PREP(4, true, true)
     CT_PREP(5, false, false) CT_PREP(5, false, true) CT_PREP(5, true, false) CT_PREP(5, true, true)
 #undef CT_PREP
+    {
+        KernelInfo& ki = eng->ki_dimers;
+        ki.smem = (size_t)ct::kDimThreads * ct::kMaxSpecies * ct::kSerStride;
+        cudaError_t e1 = cudaFuncSetAttribute(ct::ssa_dimers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem);
+        cudaError_t e2 = cudaFuncSetAttribute(ct::ssa_dimers_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                              cudaSharedmemCarveoutMaxShared);
+        cudaError_t e3 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.blocks_per_sm, ct::ssa_dimers_kernel,
+                                                                       ct::kDimThreads, ki.smem);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || ki.blocks_per_sm < 1) {
+            delete eng;
+            return fail(CT_ERR_CUDA, "dimer SSA kernel does not fit on an SM");
+        }
+    }
     *out = eng;
     return CT_OK;
 }
@@ -191,11 +222,56 @@ int ct_compile_topology(int32_t n_species, const int64_t* act, int32_t n_act, co
                         int32_t k, uint64_t* handle)
 {
     if (!handle) return fail(CT_ERR_INVALID, "handle is NULL");
-    if (k == 3) return fail(CT_ERR_UNSUPPORTED, "dimer (k=3) topologies are not implemented yet");
-    if (k != 2) return fail(CT_ERR_INVALID, "k must be 2 or 3, got %d", k);
+    if (k != 2 && k != 3) return fail(CT_ERR_INVALID, "k must be 2 or 3, got %d", k);
     if (n_species < 1) return fail(CT_ERR_INVALID, "n_species must be >= 1");
     if (n_species > CT_MAX_SPECIES) return fail(CT_ERR_UNSUPPORTED, "n_species %d > CT_MAX_SPECIES", n_species);
     if (n_act < 0 || n_inh < 0 || (n_act && !act) || (n_inh && !inh)) return fail(CT_ERR_INVALID, "bad edge arrays");
+    if (k == 3) {
+        // SPEC.md section 9: interactions numbered activations first; dimers in order of first appearance
+        if (n_act + n_inh > CT_MAX_INTERACTIONS)
+            return fail(CT_ERR_UNSUPPORTED, "%d interactions > CT_MAX_INTERACTIONS", n_act + n_inh);
+        ct::DimerTopo T;
+        memset(&T, 0, sizeof T);
+        T.n_tf = (uint8_t)n_species;
+        int per_promoter[CT_MAX_SPECIES] = {0, 0, 0, 0, 0};
+        for (int pass = 0; pass < 2; ++pass) {
+            const int64_t* e = pass ? inh : act;
+            const int n = pass ? n_inh : n_act;
+            for (int x = 0; x < n; ++x) {
+                const int64_t m1 = e[3 * x], m2 = e[3 * x + 1], tg = e[3 * x + 2];
+                if (m1 < 0 || m2 < m1 || m2 >= n_species || tg < 0 || tg >= n_species)
+                    return fail(CT_ERR_INVALID, "interaction (%lld,%lld,%lld) invalid for %d TFs (need 0 <= m1 <= m2 < n, target < n)",
+                                (long long)m1, (long long)m2, (long long)tg, n_species);
+                int d = -1;
+                for (int y = 0; y < T.n_dim; ++y)
+                    if (T.dim_a[y] == m1 && T.dim_b[y] == m2) d = y;
+                for (int y = 0; y < T.n_ixn; ++y)
+                    if (d >= 0 && T.ix_dim[y] == d && T.ix_tgt[y] == tg)
+                        return fail(CT_ERR_INVALID, "duplicate interaction (%lld,%lld,%lld)", (long long)m1, (long long)m2, (long long)tg);
+                if (d < 0) { d = T.n_dim++; T.dim_a[d] = (uint8_t)m1; T.dim_b[d] = (uint8_t)m2; }
+                T.ix_dim[T.n_ixn] = (uint8_t)d;
+                T.ix_tgt[T.n_ixn] = (uint8_t)tg;
+                T.ix_act[T.n_ixn] = pass ? 0 : 1;
+                T.n_ixn++;
+                if ((int)tg + 1 > T.n_comp) T.n_comp = (uint8_t)(tg + 1);
+                per_promoter[tg]++;
+            }
+        }
+        std::array<uint8_t, sizeof(ct::DimerTopo)> key;
+        memcpy(key.data(), &T, sizeof T);
+        std::lock_guard<std::mutex> lock(g_dimer_mutex);
+        auto it = g_dimer_index.find(key);
+        uint32_t idx;
+        if (it != g_dimer_index.end()) {
+            idx = it->second;
+        } else {
+            idx = (uint32_t)g_dimer_topos.size();
+            g_dimer_topos.push_back(T);
+            g_dimer_index[key] = idx;
+        }
+        *handle = kDimerTag | ((uint64_t)n_species << 56) | idx;
+        return CT_OK;
+    }
     uint64_t code = (uint64_t)n_species << 56;
     for (int pass = 0; pass < 2; ++pass) {
         const int64_t* e = pass ? inh : act;
@@ -227,10 +303,24 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
     cudaStream_t stream = (cudaStream_t)stream_;
     CT_CUDA(cudaSetDevice(eng->device));
 
+    const bool dimers = is_dimer_handle(handles[0]);
+    std::vector<ct::DimerTopo> topos;
+    if (dimers) {
+        topos.resize((size_t)n_jobs);
+        std::lock_guard<std::mutex> lock(g_dimer_mutex);
+        for (int j = 0; j < n_jobs; ++j) {
+            const uint64_t idx = handles[j] & 0xffffffffull;
+            if (!is_dimer_handle(handles[j]) || idx >= g_dimer_topos.size())
+                return fail(CT_ERR_INVALID, "job %d: not a dimer topology handle (a launch takes one model only)", j);
+            topos[j] = g_dimer_topos[idx];
+        }
+    }
     std::vector<ct::Job> jobs((size_t)n_jobs);
     uint64_t total = 0, tiles = 0;
     uint32_t max_nsp = 0;
     for (int j = 0; j < n_jobs; ++j) {
+        if (!dimers && is_dimer_handle(handles[j]))
+            return fail(CT_ERR_INVALID, "job %d: dimer handle in a pairwise launch (a launch takes one model only)", j);
         const uint32_t nsp = ct::topo_nspecies(handles[j]);
         if (nsp < 1 || nsp > CT_MAX_SPECIES) return fail(CT_ERR_INVALID, "job %d: bad topology handle", j);
         if (nsp > max_nsp) max_nsp = nsp;
@@ -268,7 +358,8 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
     A.series = d_series;
     A.series_stride = series_stride;
     A.log_mask = 0;
-    for (int i = 0; i < CT_N_PARAMS; ++i) {
+    A.n_params = dimers ? CT_N_PARAMS_DIMER : CT_N_PARAMS;
+    for (int i = 0; i < CT_MAX_PARAMS; ++i) {
         A.rng_lo[i] = cfg->ranges[i][0];
         A.rng_span[i] = cfg->ranges[i][1] - cfg->ranges[i][0];
         if (cfg->ranges[i][2] != 0.0f) A.log_mask |= 1u << i;
@@ -291,6 +382,7 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
     // schedule: big jobs -> one topology per warp (uniform branches); many small jobs -> mixed lanes
     bool mixed = cfg->schedule == 2;
     if (cfg->schedule == 0) mixed = n_jobs > 1 && total / (uint64_t)n_jobs < 2048;
+    if (dimers) mixed = true;   // the dimer kernel's lanes are independent: order by cost across jobs
     if (mixed) A.n_tiles = (uint32_t)((total + ct::kTile - 1) / ct::kTile);   // tiles over launch positions
 
     // longest-expected-first order (cfg->lpt): cost pre-pass + radix sort of (job, cost) keys
@@ -319,6 +411,27 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
                                                 end_bit, stream));
         eng->launches += 2;
         A.order = d_order;
+    }
+    if (dimers) {
+        ct::DimerTopo* d_topos = nullptr;
+        CT_CUDA(cudaMallocAsync((void**)&d_topos, sizeof(ct::DimerTopo) * topos.size(), stream));
+        CT_CUDA(cudaMemcpyAsync(d_topos, topos.data(), sizeof(ct::DimerTopo) * topos.size(), cudaMemcpyHostToDevice, stream));
+        const KernelInfo& kd = eng->ki_dimers;
+        const uint64_t want = (total + ct::kDimThreads - 1) / ct::kDimThreads;
+        const uint64_t cap = (uint64_t)eng->n_sm * kd.blocks_per_sm;
+        ct::ssa_dimers_kernel<<<(unsigned)(want < cap ? want : cap), ct::kDimThreads, kd.smem, stream>>>(A, d_topos);
+        CT_CUDA(cudaGetLastError());
+        eng->launches += 1;
+        // (pageable host memory: the copy above has been staged when cudaMemcpyAsync returns)
+        CT_CUDA(cudaFreeAsync(d_topos, stream));
+        CT_CUDA(cudaFreeAsync(d_jobs, stream));
+        CT_CUDA(cudaFreeAsync(d_counter, stream));
+        if (d_keys) {
+            cudaFreeAsync(d_keys, stream); cudaFreeAsync(d_keys_out, stream); cudaFreeAsync(d_slots, stream);
+            cudaFreeAsync(d_order, stream); cudaFreeAsync(d_tmp, stream);
+            if (d_job_cost) cudaFreeAsync(d_job_cost, stream);
+        }
+        return CT_OK;
     }
     const int mm = max_nsp <= 3 ? 3 : (int)max_nsp;
     bool all_full = true;
@@ -399,8 +512,9 @@ int ct_rewards_host(ct_engine* eng, const uint64_t* handles, const uint32_t* n_t
     CT_CUDA(cudaMallocAsync((void**)&d_mean, sizeof(double) * n_jobs, s));
     CT_CUDA(cudaMallocAsync((void**)&d_jev, sizeof(uint64_t) * n_jobs, s));
     if (h_params) {
-        CT_CUDA(cudaMallocAsync((void**)&d_params, sizeof(float) * total * CT_N_PARAMS, s));
-        CT_CUDA(cudaMemcpyAsync(d_params, h_params, sizeof(float) * total * CT_N_PARAMS, cudaMemcpyHostToDevice, s));
+        const size_t np = (size_t)params_per_trajectory(handles, n_jobs);
+        CT_CUDA(cudaMallocAsync((void**)&d_params, sizeof(float) * total * np, s));
+        CT_CUDA(cudaMemcpyAsync(d_params, h_params, sizeof(float) * total * np, cudaMemcpyHostToDevice, s));
     }
     int rc = ct_launch_rewards(eng, handles, n_traj, traj_base, job_cost, n_jobs, cfg, seed, s, d_params, d_reward,
                                d_lag, d_events, nullptr, 0);
@@ -445,8 +559,9 @@ int ct_rewards_submit(ct_engine* eng, const uint64_t* handles, const uint32_t* n
     CT_CUDA(cudaMallocAsync((void**)&t.d_mean, sizeof(double) * n_jobs, s));
     CT_CUDA(cudaMallocAsync((void**)&t.d_jev, sizeof(uint64_t) * n_jobs, s));
     if (h_params) {
-        CT_CUDA(cudaMallocAsync((void**)&t.d_params, sizeof(float) * t.total * CT_N_PARAMS, s));
-        CT_CUDA(cudaMemcpyAsync(t.d_params, h_params, sizeof(float) * t.total * CT_N_PARAMS, cudaMemcpyHostToDevice, s));
+        const size_t np = (size_t)params_per_trajectory(handles, n_jobs);
+        CT_CUDA(cudaMallocAsync((void**)&t.d_params, sizeof(float) * t.total * np, s));
+        CT_CUDA(cudaMemcpyAsync(t.d_params, h_params, sizeof(float) * t.total * np, cudaMemcpyHostToDevice, s));
     }
     int rc = ct_launch_rewards(eng, handles, n_traj, traj_base, job_cost, n_jobs, cfg, seed, s, t.d_params, t.d_reward,
                                t.d_lag, t.d_events, nullptr, 0);

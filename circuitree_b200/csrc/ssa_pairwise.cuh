@@ -36,7 +36,7 @@ struct LaunchArgs {
     uint32_t n_jobs;
     uint32_t n_tiles;
     uint32_t* tile_counter;          // zeroed before launch
-    const float* params;             // nullable [total][10]
+    const float* params;             // nullable [total][n_params]
     float* reward;
     int32_t* lag;                    // nullable
     uint32_t* events;                // nullable
@@ -45,9 +45,10 @@ struct LaunchArgs {
     unsigned long long* warp_iters;  // nullable debug counter: hot-loop iterations (2 steps each) summed over warps
     const uint32_t* order;           // nullable: launch position -> output slot, longest expected first
     uint32_t total;                  // trajectories in the launch
-    float rng_lo[10];
-    float rng_span[10];
+    float rng_lo[12];
+    float rng_span[12];
     uint32_t log_mask;
+    int32_t n_params;                // 10 (pairwise, SPEC.md section 4) or 12 (dimers, section 9)
     uint32_t seed_lo, seed_hi;
     uint32_t rk[20];                 // Philox round keys (k0 + r*W0, k1 + r*W1), r = 0..9
     int32_t nt, decim, n_dec;
@@ -326,9 +327,9 @@ __device__ __forceinline__ void trajectory_params(const LaunchArgs& A, uint32_t 
                                                   float (&p)[12])
 {
     if (A.params) {
-        const float* src = A.params + (size_t)out * 10;
+        const float* src = A.params + (size_t)out * A.n_params;
 #pragma unroll
-        for (int i = 0; i < 10; ++i) p[i] = src[i];
+        for (int i = 0; i < 12; ++i) p[i] = (i < A.n_params) ? src[i] : 0.0f;
         return;
     }
 #pragma unroll
@@ -337,7 +338,7 @@ __device__ __forceinline__ void trajectory_params(const LaunchArgs& A, uint32_t 
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
             const int i = 4 * blk + w;
-            if (i < 10) {
+            {
                 float v = A.rng_lo[i] + u01(x.w[w]) * A.rng_span[i];
                 p[i] = ((A.log_mask >> i) & 1u) ? exp2f(v * 3.32192809489f) : v;
             }

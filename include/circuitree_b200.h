@@ -20,7 +20,10 @@
 extern "C" {
 #endif
 
-#define CT_N_PARAMS 10       /* SPEC.md section 4 */
+#define CT_N_PARAMS 10       /* pairwise model, SPEC.md section 4 */
+#define CT_N_PARAMS_DIMER 12 /* dimer model, SPEC.md section 9: + k_dim, k_undim */
+#define CT_MAX_PARAMS 12
+#define CT_MAX_INTERACTIONS 10 /* dimer model: interactions (and distinct dimers) per topology */
 #define CT_MAX_SPECIES 5     /* GPU path: components per state */
 #define CT_MAX_NDEC 126      /* decimated samples kept per species (128 shared-memory bytes each) */
 
@@ -42,7 +45,8 @@ typedef struct ct_sim_config {
                                 (many small jobs).  Results are identical, only the speed differs. */
     int32_t lpt;             /* 1 (default): start trajectories longest-expected-first (cost pre-pass +
                                 radix sort); 0: in id order.  Results are identical. */
-    float ranges[CT_N_PARAMS][3]; /* (lo, hi, is_log) per parameter, SPEC.md section 4 */
+    float ranges[CT_MAX_PARAMS][3]; /* (lo, hi, is_log) per parameter, SPEC.md sections 4 and 9
+                                (rows 10, 11 = k_dim, k_undim are used by dimer topologies only) */
 } ct_sim_config;
 
 typedef struct ct_engine ct_engine;   /* opaque; one per device */
@@ -63,8 +67,14 @@ int ct_engine_info(ct_engine *eng, int32_t *n_sm, int32_t *resident_lanes);
 /*
  * Compile one topology from parse_genotype output (models.py:441-480): `act` and `inh` are
  * int64 [n][k] row-major index arrays, k = 2 for SimpleNetworkGrammar ((regulator, target)).
- * k = 3 (DimersGrammar, models.py:844-884) returns CT_ERR_UNSUPPORTED in this round.
- * The handle is a self-contained 64-bit code; it needs no release.
+ * The k = 2 handle is a self-contained 64-bit code.
+ * k = 3 (DimersGrammar, models.py:844-884): rows are (monomer1 <= monomer2, target), indices into
+ * components + regulators, n_species = number of components + regulators (a TF that is never a
+ * target is expressed constitutively, which is what SPEC.md section 9 says of regulators).  The
+ * handle (bit 63 set) names an entry of a process-wide, append-only topology table; equal
+ * topologies get equal handles.  Neither kind of handle needs a release.
+ * A launch takes pairwise handles only or dimer handles only (CT_ERR_INVALID otherwise); explicit
+ * parameter rows are CT_N_PARAMS wide for pairwise and CT_N_PARAMS_DIMER wide for dimer launches.
  */
 int ct_compile_topology(int32_t n_species, const int64_t *act, int32_t n_act,
                         const int64_t *inh, int32_t n_inh, int32_t k, uint64_t *handle);
@@ -73,7 +83,7 @@ int ct_compile_topology(int32_t n_species, const int64_t *act, int32_t n_act,
  * Device-buffer launch.  Job j simulates n_traj[j] trajectories of topology handles[j]; its
  * trajectory ids are traj_base[j] .. traj_base[j]+n_traj[j]-1 and its outputs occupy the slots
  * after those of jobs 0..j-1.  All d_* pointers are device pointers on the engine's device:
- *   d_params  (nullable) float32 [total][CT_N_PARAMS] explicit parameters, else sampled in-kernel
+ *   d_params  (nullable) float32 [total][CT_N_PARAMS or CT_N_PARAMS_DIMER] explicit parameters, else sampled in-kernel
  *   d_reward  float32 [total]     d_lag  int32 [total] (nullable)   d_events uint32 [total] (nullable)
  *   d_series  (nullable, debug) uint8 [total][n_species_max][nt/decim] companded block sums
  * `stream` is a cudaStream_t (0 = default stream).  Asynchronous.

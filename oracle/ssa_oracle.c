@@ -27,6 +27,8 @@
 
 #define CT_MAX_SPECIES 8
 #define CT_N_PARAMS 10
+#define CT_N_PARAMS_DIMER 12
+#define CT_MAX_IXN 10
 
 /* ---- SPEC.md §3: Philox4x32-10 counter-based RNG ------------------------- */
 static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
@@ -83,6 +85,17 @@ static uint32_t rng_next(rng_t *g)
 /* ---- SPEC.md §4: parameter vector from (lo, hi, is_log) ranges ----------- */
 /* params: 0 k_on, 1 k_off1, 2 k_off2, 3 km_unbound, 4 km_act, 5 km_rep,
  *         6 km_act_rep, 7 kp, 8 gamma_m, 9 gamma_p                         */
+static void sample_params_n(rng_t *g, const double *ranges /* [n][3] */, double *p, int n)
+{
+    for (int i = 0; i < n; ++i) {
+        double u = u01(rng_next(g));
+        double lo = ranges[3 * i], hi = ranges[3 * i + 1];
+        double v = lo + u * (hi - lo);
+        p[i] = ranges[3 * i + 2] != 0.0 ? pow(10.0, v) : v;
+    }
+    for (int i = n; i < 12; ++i) (void)rng_next(g);   /* the setup block ends at word 12 */
+}
+
 static void sample_params(rng_t *g, const double *ranges /* [10][3] */, double *p)
 {
     for (int i = 0; i < CT_N_PARAMS; ++i) {
@@ -330,6 +343,126 @@ int ct_oracle_run_pairwise(int n_species,
         if (pthread_create(&th[started], NULL, worker, &job) == 0) ++started;
     if (started == 0) worker(&job);
     for (int i = 0; i < started; ++i) pthread_join(th[i], NULL);
+    return 0;
+}
+
+
+/* ---- SPEC.md section 9: dimer model ------------------------------------------------------------ */
+typedef struct {
+    int n_tf, n_comp, n_ixn, n_dim;
+    int dim_a[CT_MAX_IXN], dim_b[CT_MAX_IXN];
+    int ix_dim[CT_MAX_IXN], ix_tgt[CT_MAX_IXN], ix_act[CT_MAX_IXN];
+} dimer_topo_t;
+
+static uint64_t simulate_dimers(const dimer_topo_t *T, const sim_cfg_t *cfg, const double *prm, uint64_t seed,
+                                uint64_t traj, rng_t *setup, uint8_t *q)
+{
+    const int M = T->n_tf, n_dec = cfg->nt / cfg->decim;
+    const double k_on = prm[0], k_off1 = prm[1], k_off2 = prm[2];
+    const double km[4] = { prm[3], prm[4], prm[5], prm[6] };
+    const double kp = prm[7], gm = prm[8], gp = prm[9], k_dim = prm[10], k_undim = prm[11];
+    double P[CT_MAX_SPECIES], R[CT_MAX_SPECIES], D[CT_MAX_IXN];
+    int b[CT_MAX_IXN];
+    for (int s = 0; s < M; ++s) { R[s] = 0.0; P[s] = (double)poisson_inv(u01(rng_next(setup)), cfg->init_mean); }
+    for (int d = 0; d < CT_MAX_IXN; ++d) { D[d] = 0.0; b[d] = 0; }
+    rng_t g; rng_init(&g, seed, traj, 1u);
+    double block[CT_MAX_SPECIES] = {0};
+    int k = 0; double t = 0.0; uint64_t n_events = 0;
+    double a[4 * CT_MAX_SPECIES + 4 * CT_MAX_IXN];
+    for (;;) {
+        int nr = 0; double a0 = 0.0;
+        for (int s = 0; s < M; ++s) {
+            int n = 0, na = 0, ni = 0;
+            for (int e = 0; e < T->n_ixn; ++e) if (T->ix_tgt[e] == s) { n += b[e]; if (T->ix_act[e]) na += b[e]; else ni += b[e]; }
+            a[nr++] = (s < T->n_comp) ? km[(na > 0) | ((ni > 0) << 1)] : km[0];
+            a[nr++] = gm * R[s]; a[nr++] = kp * R[s]; a[nr++] = gp * P[s];
+            if (s < T->n_comp) {
+                double koff = (n >= 2) ? k_off2 : k_off1;
+                for (int e = 0; e < T->n_ixn; ++e) if (T->ix_tgt[e] == s) a[nr++] = k_on * D[T->ix_dim[e]] * (double)(2 - n);
+                for (int e = 0; e < T->n_ixn; ++e) if (T->ix_tgt[e] == s) a[nr++] = koff * (double)b[e];
+            }
+        }
+        for (int d = 0; d < T->n_dim; ++d) {
+            int x = T->dim_a[d], y = T->dim_b[d];
+            a[nr++] = (x != y) ? k_dim * P[x] * P[y] : k_dim * P[x] * (P[x] - 1.0) * 0.5;
+            a[nr++] = k_undim * D[d];
+        }
+        for (int r = 0; r < nr; ++r) a0 += a[r];
+        double u1 = u01(rng_next(&g)), u2 = u01(rng_next(&g));
+        double t_new = (a0 > 0.0) ? t - log(u1) / a0 : INFINITY;
+        while (k < cfg->nt && (double)k * cfg->dt < t_new) {
+            for (int s = 0; s < M; ++s) block[s] += (P[s] > cfg->sample_cap) ? cfg->sample_cap : P[s];
+            ++k;
+            if (k % cfg->decim == 0) {
+                int kd = k / cfg->decim - 1;
+                if (kd < n_dec) for (int s = 0; s < M; ++s) { q[s * n_dec + kd] = compand(block[s]); block[s] = 0.0; }
+            }
+        }
+        if (k >= cfg->nt) break;
+        t = t_new;
+        double target = u2 * a0, c = 0.0; int sel = -1;
+        for (int r = 0; r < nr; ++r) { c += a[r]; if (target < c) { sel = r; break; } }
+        nr = 0;
+        for (int s = 0; s < M && sel >= 0; ++s) {
+            if (sel == nr++) { R[s] += 1.0; sel = -1; break; }
+            if (sel == nr++) { R[s] -= 1.0; sel = -1; break; }
+            if (sel == nr++) { P[s] += 1.0; sel = -1; break; }
+            if (sel == nr++) { P[s] -= 1.0; sel = -1; break; }
+            if (s < T->n_comp) {
+                for (int e = 0; e < T->n_ixn && sel >= 0; ++e)
+                    if (T->ix_tgt[e] == s && sel == nr++) { D[T->ix_dim[e]] -= 1.0; b[e] += 1; sel = -1; }
+                for (int e = 0; e < T->n_ixn && sel >= 0; ++e)
+                    if (T->ix_tgt[e] == s && sel == nr++) { D[T->ix_dim[e]] += 1.0; b[e] -= 1; sel = -1; }
+            }
+        }
+        for (int d = 0; d < T->n_dim && sel >= 0; ++d) {
+            int x = T->dim_a[d], y = T->dim_b[d];
+            if (sel == nr++) { P[x] -= 1.0; P[y] -= 1.0; D[d] += 1.0; sel = -1; break; }
+            if (sel == nr++) { P[x] += 1.0; P[y] += 1.0; D[d] -= 1.0; sel = -1; break; }
+        }
+        ++n_events;
+    }
+    return n_events;
+}
+
+/* act / inh: int32 [n][3] rows (monomer1, monomer2, target) as DimersGrammar.parse_genotype returns
+ * them (reference circuitree/models.py:844-884); ranges [12][3].  Single-threaded. */
+int ct_oracle_run_dimers(int n_tf, int n_comp, const int32_t *act, int n_act, const int32_t *inh, int n_inh,
+                         const double *ranges, const double *explicit_params, uint64_t seed, uint64_t traj_base,
+                         int64_t n_traj, int nt, int decim, double dt, double init_mean,
+                         float *reward, int32_t *lag, uint64_t *n_events, uint8_t *series)
+{
+    if (n_tf < 1 || n_tf > 5 || n_comp < 1 || n_comp > n_tf || n_act + n_inh > CT_MAX_IXN || nt / decim > 512) return 1;
+    dimer_topo_t T; memset(&T, 0, sizeof T);
+    T.n_tf = n_tf; T.n_comp = n_comp;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int32_t *x = pass ? inh : act; int n = pass ? n_inh : n_act;
+        for (int e = 0; e < n; ++e) {
+            int m1 = x[3 * e], m2 = x[3 * e + 1], tg = x[3 * e + 2];
+            if (m1 < 0 || m2 < m1 || m2 >= n_tf || tg < 0 || tg >= n_comp) return 2;
+            int d = -1;
+            for (int y = 0; y < T.n_dim; ++y) if (T.dim_a[y] == m1 && T.dim_b[y] == m2) d = y;
+            if (d < 0) { d = T.n_dim++; T.dim_a[d] = m1; T.dim_b[d] = m2; }
+            T.ix_dim[T.n_ixn] = d; T.ix_tgt[T.n_ixn] = tg; T.ix_act[T.n_ixn] = pass ? 0 : 1; T.n_ixn++;
+        }
+    }
+    sim_cfg_t cfg = { n_tf, nt, decim, dt, init_mean, 4095.0 };
+    const int n_dec = nt / decim;
+    for (int64_t x = 0; x < n_traj; ++x) {
+        uint64_t traj = traj_base + (uint64_t)x;
+        rng_t setup; rng_init(&setup, seed, traj, 0u);
+        double prm[CT_N_PARAMS_DIMER];
+        sample_params_n(&setup, ranges, prm, CT_N_PARAMS_DIMER);
+        if (explicit_params) memcpy(prm, explicit_params + x * CT_N_PARAMS_DIMER, sizeof prm);
+        uint8_t qbuf[CT_MAX_SPECIES * 512];
+        uint8_t *q = series ? series + (size_t)x * n_tf * n_dec : qbuf;
+        uint64_t ne = simulate_dimers(&T, &cfg, prm, seed, traj, &setup, q);
+        int lg = 0;
+        double rw = ct_oracle_reward_from_series(q, n_tf, n_dec, &lg);
+        if (reward) reward[x] = (float)rw;
+        if (lag) lag[x] = lg;
+        if (n_events) n_events[x] = ne;
+    }
     return 0;
 }
 

@@ -46,6 +46,13 @@ def lib() -> ctypes.CDLL:
             ctypes.c_int,
             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
         ]
+        L.ct_oracle_run_dimers.restype = ctypes.c_int
+        L.ct_oracle_run_dimers.argtypes = [
+            ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int64,
+            ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+        ]
         L.ct_oracle_reward_from_series.restype = ctypes.c_double
         L.ct_oracle_reward_from_series.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         L.ct_oracle_philox.restype = None
@@ -113,3 +120,46 @@ def reward_from_series(q: np.ndarray):
     lag = ctypes.c_int(0)
     r = lib().ct_oracle_reward_from_series(q.ctypes.data, q.shape[0], q.shape[1], ctypes.byref(lag))
     return float(r), int(lag.value)
+
+
+N_PARAMS_DIMER = 12
+
+
+def run_dimers(n_tf, n_comp, activations, inhibitions, ranges, n_traj, *, seed=0, traj_base=0, explicit_params=None,
+               nt=2000, decim=16, dt=20.0, init_mean=10.0, want_series=False, n_threads=1):
+    """Dimer model (SPEC.md section 9).  ``activations`` / ``inhibitions`` are the int[n,3] arrays of
+    ``DimersGrammar.parse_genotype`` (reference circuitree/models.py:844-884).  ``n_threads`` > 1 splits
+    the trajectory range over Python threads (the C call releases the GIL)."""
+    act = np.ascontiguousarray(np.asarray(activations, dtype=np.int32).reshape(-1, 3))
+    inh = np.ascontiguousarray(np.asarray(inhibitions, dtype=np.int32).reshape(-1, 3))
+    rng = np.ascontiguousarray(np.asarray(ranges, dtype=np.float64).reshape(N_PARAMS_DIMER, 3))
+    exp = None
+    if explicit_params is not None:
+        exp = np.ascontiguousarray(np.asarray(explicit_params, dtype=np.float64).reshape(n_traj, N_PARAMS_DIMER))
+    n_dec = nt // decim
+    reward = np.zeros(n_traj, dtype=np.float32)
+    lag = np.zeros(n_traj, dtype=np.int32)
+    n_events = np.zeros(n_traj, dtype=np.uint64)
+    series = np.zeros((n_traj, n_tf, n_dec), dtype=np.uint8) if want_series else None
+
+    def work(a, b):
+        rc = lib().ct_oracle_run_dimers(
+            n_tf, n_comp, _ptr(act), act.shape[0], _ptr(inh), inh.shape[0], _ptr(rng),
+            None if exp is None else exp[a:b].ctypes.data, seed, traj_base + a, b - a, nt, decim, dt, init_mean,
+            reward[a:b].ctypes.data, lag[a:b].ctypes.data, n_events[a:b].ctypes.data,
+            None if series is None else series[a:b].ctypes.data)
+        if rc != 0:
+            raise ValueError(f"ct_oracle_run_dimers failed with code {rc}")
+
+    if n_threads <= 1 or n_traj < 2 * n_threads:
+        work(0, n_traj)
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+
+        cuts = np.linspace(0, n_traj, n_threads * 4 + 1).astype(int)
+        with ThreadPoolExecutor(n_threads) as ex:
+            list(ex.map(lambda ab: work(*ab), zip(cuts[:-1], cuts[1:])))
+    out = {"reward": reward, "lag": lag, "n_events": n_events}
+    if want_series:
+        out["series"] = series
+    return out

@@ -41,6 +41,7 @@ def test_default_config_matches_spec_constants():
     assert (cfg.nt, cfg.decim) == (d["nt"], d["decim"])
     assert cfg.dt == d["dt"] and cfg.init_mean == d["init_mean"]
     assert np.allclose(cfg.ranges_array(), np.array(d["ranges"]), atol=1e-6)
+    assert np.allclose(cfg.ranges_array(12), np.array(d["ranges"] + d["dimer_ranges"]), atol=1e-6)
     assert cfg.n_dec == 125 <= _capi.MAX_NDEC
 
 
@@ -56,8 +57,28 @@ def test_compile_topology_validation_without_gpu():
         _capi.compile_topology(3, [(0, 1)], [(0, 1)])          # duplicate edge
     with pytest.raises(_capi.EngineError):
         _capi.compile_topology(6, [], [])                       # too many species for the GPU path
+
+
+def test_compile_dimer_topology_without_gpu():
+    """k = 3 rows (monomer1 <= monomer2, target) as DimersGrammar.parse_genotype returns them
+    (reference circuitree/models.py:844-884)."""
+    from circuitree_b200 import DimersGrammar
+
+    g = DimersGrammar(components=["A", "B", "C"], regulators=["R"], interactions=["activates", "inhibits"])
+    comps, regs, act, inh = g.parse_genotype("*ABC+R::ARaB_BBiC_CCiA")
+    h = _capi.compile_topology(len(comps) + len(regs), act, inh, k=3)
+    assert _capi.is_dimer_handle(h) and (h >> 56) & 15 == 4
+    assert _capi.compile_topology(4, act, inh, k=3) == h                  # equal topologies share a handle
+    assert _capi.compile_topology(4, inh, act, k=3) != h
+    assert not _capi.is_dimer_handle(_capi.compile_topology(3, [], [(0, 1)]))
     with pytest.raises(_capi.EngineError):
-        _capi.compile_topology(3, [(0, 1, 2)], [], k=3)         # dimers: not in this round
+        _capi.compile_topology(3, [(1, 0, 2)], [], k=3)         # monomers must be sorted
+    with pytest.raises(_capi.EngineError):
+        _capi.compile_topology(3, [(0, 3, 2)], [], k=3)         # monomer out of range
+    with pytest.raises(_capi.EngineError):
+        _capi.compile_topology(3, [(0, 1, 2)], [(0, 1, 2)], k=3)   # duplicate interaction
+    with pytest.raises(_capi.EngineError):
+        _capi.compile_topology(3, [(0, 0, 0)] * 11, [], k=3)     # more than CT_MAX_INTERACTIONS
 
 
 def test_no_cpu_fallback():

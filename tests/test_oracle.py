@@ -104,3 +104,51 @@ def test_invalid_inputs():
         so.run_pairwise(3, [(0, 5)], [], RANGES, 1)
     with pytest.raises(ValueError):
         so.run_pairwise(9, [], [], RANGES, 1)
+
+
+# ---- dimer model (SPEC.md section 9) ---------------------------------------------------------------------
+DIMER_RANGES = RANGES + [(-5.3, -4.7, 1), (-2.8, -2.2, 1)]
+HOMODIMER_REPRESSILATOR = ([], [(0, 0, 1), (1, 1, 2), (2, 2, 0)])
+
+
+def test_dimer_checker_is_deterministic_and_thread_independent():
+    act, inh = HOMODIMER_REPRESSILATOR
+    a = so.run_dimers(3, 3, act, inh, DIMER_RANGES, 24, seed=5, nt=320, want_series=True)
+    b = so.run_dimers(3, 3, act, inh, DIMER_RANGES, 24, seed=5, nt=320, want_series=True, n_threads=4)
+    for k in ("reward", "lag", "n_events", "series"):
+        assert np.array_equal(a[k], b[k]), k
+    c = so.run_dimers(3, 3, act, inh, DIMER_RANGES, 8, seed=5, traj_base=16, nt=320)
+    assert np.array_equal(c["n_events"], a["n_events"][16:])
+
+
+def test_dimer_model_without_interactions_is_constitutive_expression():
+    """No interactions: no dimer species exist, every TF sits at km kp / (gm gp); and the pairwise
+    and dimer models then describe the same process (same streams: identical records)."""
+    p = np.tile([0.0, 0.2, 0.004, 0.5, 0.5, 0.5, 0.5, 0.05, 0.02, 0.005, 2e-5, 2e-3], (48, 1))
+    d = so.run_dimers(4, 3, [], [], DIMER_RANGES, 48, seed=2, explicit_params=p, want_series=True)
+    level = (d["series"][:, :, 60:].astype(float) ** 2 / 16).mean(axis=(0, 2))
+    assert np.all((230 < level) & (level < 270)), level
+    q = so.run_pairwise(4, [], [], RANGES, 48, seed=2, explicit_params=p[:, :10], want_series=True)
+    assert np.array_equal(d["series"], q["series"]) and np.array_equal(d["n_events"], q["n_events"])
+
+
+def test_dimer_pool_and_oscillation():
+    p = np.tile([0.0, 0.2, 0.004, 0.5, 0.5, 0.5, 0.5, 0.05, 0.02, 0.005, 2e-5, 2e-3], (48, 1))
+    d = so.run_dimers(3, 3, [], [(0, 0, 1)], DIMER_RANGES, 48, seed=3, explicit_params=p, want_series=True, n_threads=4)
+    level = (d["series"][:, :, 60:].astype(float) ** 2 / 16).mean(axis=(0, 2))
+    # k_on = 0 and free dimers do not decay (SPEC.md section 9): the AA pool is in detailed balance with the
+    # monomers, so every mean monomer level stays at 250; the pool only adds (un)dimerisation events
+    assert np.all((230 < level) & (level < 270)), level
+    base = so.run_dimers(3, 3, [], [], DIMER_RANGES, 48, seed=3, explicit_params=p)
+    assert d["n_events"].mean() > 1.08 * base["n_events"].mean()
+    act, inh = HOMODIMER_REPRESSILATOR
+    osc = so.run_dimers(3, 3, act, inh, DIMER_RANGES, 64, seed=4, n_threads=8)
+    flat = so.run_dimers(3, 3, [], [], DIMER_RANGES, 64, seed=4, n_threads=8)
+    assert osc["reward"].mean() > 0.6 and flat["reward"].mean() < 0.3
+
+
+def test_dimer_checker_rejects_bad_topologies():
+    with pytest.raises(ValueError):
+        so.run_dimers(3, 3, [(1, 0, 2)], [], DIMER_RANGES, 1)      # monomers not sorted
+    with pytest.raises(ValueError):
+        so.run_dimers(3, 2, [(0, 1, 2)], [], DIMER_RANGES, 1)      # target is not a component
