@@ -77,6 +77,7 @@ struct ct_engine {
     int n_sm = 0;
     cudaStream_t stream = nullptr;   // used by the host-buffer entry points
     KernelInfo ki[3][2][2];         // [M-3][mixed][all jobs have M species]
+    KernelInfo ki_fast[3];          // [M-3]: every gene has at most one regulator (ssa_step kFast)
     KernelInfo ki_dimers;
     int64_t launches = 0;
     unsigned long long* d_warp_iters = nullptr;   // debug counter (ct_engine_warp_iterations)
@@ -84,14 +85,14 @@ struct ct_engine {
 
 namespace {
 
-template <int MM, bool kMixed, bool kAll>
+template <int MM, bool kMixed, bool kAll, bool kFast = false>
 int prepare_kernel(KernelInfo& ki)
 {
     ki.smem = (size_t)ct::kThreads * MM * ct::kSerStride + (ct::kThreads / 32) * ct::kSerStride * sizeof(float);
-    CT_CUDA(cudaFuncSetAttribute(ct::ssa_pairwise_kernel<MM, kMixed, kAll>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
-    CT_CUDA(cudaFuncSetAttribute(ct::ssa_pairwise_kernel<MM, kMixed, kAll>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    CT_CUDA(cudaFuncSetAttribute(ct::ssa_pairwise_kernel<MM, kMixed, kAll, kFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
+    CT_CUDA(cudaFuncSetAttribute(ct::ssa_pairwise_kernel<MM, kMixed, kAll, kFast>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared));
-    CT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.blocks_per_sm, ct::ssa_pairwise_kernel<MM, kMixed, kAll>, ct::kThreads,
+    CT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.blocks_per_sm, ct::ssa_pairwise_kernel<MM, kMixed, kAll, kFast>, ct::kThreads,
                                                           ki.smem));
     if (ki.blocks_per_sm < 1) return fail(CT_ERR_CUDA, "SSA kernel (M=%d) does not fit on an SM", MM);
     return CT_OK;
@@ -106,6 +107,7 @@ int validate_cfg(const ct_sim_config* cfg)
     if (!(cfg->init_mean >= 0.0f) || cfg->init_mean > 80.0f) return fail(CT_ERR_INVALID, "init_mean out of range [0, 80]");
     if (cfg->schedule < 0 || cfg->schedule > 2) return fail(CT_ERR_INVALID, "schedule must be 0 (auto), 1 (uniform) or 2 (mixed)");
     if (cfg->lpt < 0 || cfg->lpt > 1) return fail(CT_ERR_INVALID, "lpt must be 0 or 1");
+    if (cfg->fast_path < 0 || cfg->fast_path > 1) return fail(CT_ERR_INVALID, "fast_path must be 0 or 1");
     return CT_OK;
 }
 
@@ -130,6 +132,7 @@ int ct_default_config(ct_sim_config* cfg)
     cfg->init_mean = 10.0f;
     cfg->schedule = 0;
     cfg->lpt = 1;
+    cfg->fast_path = 1;
     memcpy(cfg->ranges, r, sizeof r);
     return CT_OK;
 }
@@ -160,6 +163,9 @@ int ct_engine_create(int device, ct_engine** out)
     CT_PREP(4, false, false) CT_PREP(4, false, true) CT_PREP(4, true, false) CT_PREP(4, true, true)
     CT_PREP(5, false, false) CT_PREP(5, false, true) CT_PREP(5, true, false) CT_PREP(5, true, true)
 #undef CT_PREP
+    if ((rc = prepare_kernel<3, false, true, true>(eng->ki_fast[0])) != CT_OK) { delete eng; return rc; }
+    if ((rc = prepare_kernel<4, false, true, true>(eng->ki_fast[1])) != CT_OK) { delete eng; return rc; }
+    if ((rc = prepare_kernel<5, false, true, true>(eng->ki_fast[2])) != CT_OK) { delete eng; return rc; }
     {
         KernelInfo& ki = eng->ki_dimers;
         ki.smem = (size_t)ct::kDimThreads * ct::kMaxSpecies * ct::kSerStride;
@@ -436,14 +442,25 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
     const int mm = max_nsp <= 3 ? 3 : (int)max_nsp;
     bool all_full = true;
     for (int j = 0; j < n_jobs; ++j) all_full = all_full && (ct::topo_nspecies(handles[j]) == (uint32_t)mm || n_traj[j] == 0);
-    const KernelInfo& ki = eng->ki[mm - 3][mixed ? 1 : 0][all_full ? 1 : 0];
+    // every gene of every job has at most one regulator -> the specialised hot loop (same results)
+    bool fast = !mixed && all_full && cfg->fast_path != 0;
+    for (int j = 0; j < n_jobs && fast; ++j) {
+        if (n_traj[j] == 0) continue;
+        for (int t = 0; t < mm; ++t) {
+            int indeg = 0;
+            for (int i = 0; i < mm; ++i) indeg += ct::topo_edge(handles[j], i, t) != 0u;
+            if (indeg > 1) fast = false;
+        }
+    }
+    const KernelInfo& ki = fast ? eng->ki_fast[mm - 3] : eng->ki[mm - 3][mixed ? 1 : 0][all_full ? 1 : 0];
     uint64_t want_blocks = (total + ct::kThreads - 1) / ct::kThreads;
     uint64_t max_blocks = (uint64_t)eng->n_sm * ki.blocks_per_sm;
     const unsigned grid = (unsigned)(want_blocks < max_blocks ? want_blocks : max_blocks);
 #define CT_LAUNCH(MM, MIXED, ALL) ct::ssa_pairwise_kernel<MM, MIXED, ALL><<<grid, ct::kThreads, ki.smem, stream>>>(A)
 #define CT_LAUNCH_M(MM)                                                          \
     do {                                                                         \
-        if (mixed) { if (all_full) CT_LAUNCH(MM, true, true); else CT_LAUNCH(MM, true, false); }     \
+        if (fast) ct::ssa_pairwise_kernel<MM, false, true, true><<<grid, ct::kThreads, ki.smem, stream>>>(A);   \
+        else if (mixed) { if (all_full) CT_LAUNCH(MM, true, true); else CT_LAUNCH(MM, true, false); }     \
         else { if (all_full) CT_LAUNCH(MM, false, true); else CT_LAUNCH(MM, false, false); }         \
     } while (0)
     if (mm == 3) CT_LAUNCH_M(3); else if (mm == 4) CT_LAUNCH_M(4); else CT_LAUNCH_M(5);

@@ -153,6 +153,8 @@ template <int MM>
 struct Lane {
     float P[MM], R[MM], b[MM][MM];
     float n[MM], A[MM];      // bound molecules at promoter j: total, and on activating edges
+    float h[MM][MM];         // kFast only: 1.0f where edge i->j exists (each gene has at most one regulator)
+    float kmb[MM];           // kFast only: transcription rate of gene j with its regulator bound (km_act or km_rep)
     float blk[MM];
     float k_on, k_off1, k_off2, km0, km1, km2, km3, kp, gm, gp;
     float t_rem;
@@ -189,7 +191,7 @@ __device__ __forceinline__ void lane_park(Lane<MM>& L)
     L.k_on = L.k_off1 = L.k_off2 = L.km0 = L.km1 = L.km2 = L.km3 = L.kp = L.gm = L.gp = 0.0f;
 #pragma unroll
     for (int j = 0; j < MM; ++j) {
-        L.P[j] = L.R[j] = L.blk[j] = L.n[j] = L.A[j] = 0.0f;
+        L.P[j] = L.R[j] = L.blk[j] = L.n[j] = L.A[j] = L.kmb[j] = 0.0f;
 #pragma unroll
         for (int i = 0; i < MM; ++i) L.b[i][j] = 0.0f;
     }
@@ -209,10 +211,18 @@ __device__ __forceinline__ void lane_park(Lane<MM>& L)
 // in a block that only runs when some lane of the warp fired a (un)binding at that gene.  This is
 // the same direct method: the flat reaction is the one whose running sum first exceeds the target.
 //
-// Selection: s_r = [target < c_r] is monotone along the running sum, so reaction r fires iff
-// s_r - s_{r-1} = 1 and the state updates are differences of neighbouring s values; a reaction with
-// zero propensity has c_r = c_{r-1} and can never fire.
-template <int MM, bool kAllSpecies>
+// The running sum is kept per gene (M independent chains of six instead of one chain of 6M): gene
+// j's entries are lc[6j..6j+5], its total g_j, a0 = ((g_0 + g_1) + ...).  Selection walks the genes
+// with t_0 = u a0, t_{j+1} = t_j - g_j and compares t_j with gene j's local sums.  IEEE subtraction
+// keeps the sign exact (t_j < g_j  <=>  t_{j+1} < 0), so s_r = [t_j < lc_r] is monotone along the
+// whole flat reaction list: reaction r fires iff s_r - s_{r-1} = 1, the state updates are
+// differences of neighbouring s values, and a reaction with zero propensity can never fire.
+//
+// kFast (every gene has at most one regulator; one topology per warp; every job has MM species):
+// the regulator of a lumped (un)binding is known, so there is no resolution block and no warp vote;
+// the edge matrix is the 0/1 float matrix L.h (sum_i h_ij P_i, P_i -= h_ij d: FMA pipe, no
+// predicates), b_ij == n_j and A_j == n_j or 0 are not tracked.  Bit-identical to the general path.
+template <int MM, bool kAllSpecies, bool kFast>
 __device__ __forceinline__ void ssa_step(Lane<MM>& L, bool& active, bool& finished, const uint32_t pres,
                                          const uint32_t actm, const int nsp_in, uint32_t w_tau, uint32_t w_sel,
                                          uint8_t* ser, const int nt, const int decim, const float dt)
@@ -220,31 +230,43 @@ __device__ __forceinline__ void ssa_step(Lane<MM>& L, bool& active, bool& finish
     const int nsp = kAllSpecies ? MM : nsp_in;   // kAllSpecies: every job has MM species, no per-gene tests
     auto has = [&](int i, int j) -> bool { return (pres >> (i * kTopoStride + j)) & 1u; };
     auto is_act = [&](int i, int j) -> bool { return (actm >> (i * kTopoStride + j)) & 1u; };
-    // ---- propensities as one running sum ----
-    float cum[6 * MM], S[MM], kfree[MM], koff[MM];
-    float c = 0.0f;
+    // ---- propensities: one running sum per gene ----
+    float lc[6 * MM], g[MM], S[MM], kfree[MM], koff[MM];
 #pragma unroll
     for (int j = 0; j < MM; ++j) {
+        g[j] = 0.0f;
         if (j < nsp) {   // (entries of absent genes stay unset: pass 2 never consults them)
-            const float n = L.n[j], na = L.A[j];
-            const float km_a = (na > 0.0f) ? L.km1 : L.km0;
-            const float km_i = (na > 0.0f) ? L.km3 : L.km2;
-            c += (n > na) ? km_i : km_a;     cum[6 * j + 0] = c;
-            c = fmaf(L.gm, L.R[j], c);       cum[6 * j + 1] = c;
-            c = fmaf(L.kp, L.R[j], c);       cum[6 * j + 2] = c;
-            c = fmaf(L.gp, L.P[j], c);       cum[6 * j + 3] = c;
+            const float n = L.n[j];
+            float c;
+            if (kFast) {
+                c = (n > 0.0f) ? L.kmb[j] : L.km0;
+            } else {
+                const float na = L.A[j];
+                const float km_a = (na > 0.0f) ? L.km1 : L.km0;
+                const float km_i = (na > 0.0f) ? L.km3 : L.km2;
+                c = (n > na) ? km_i : km_a;
+            }
+            lc[6 * j + 0] = c;
+            c = fmaf(L.gm, L.R[j], c);       lc[6 * j + 1] = c;
+            c = fmaf(L.kp, L.R[j], c);       lc[6 * j + 2] = c;
+            c = fmaf(L.gp, L.P[j], c);       lc[6 * j + 3] = c;
             float sp = 0.0f;
 #pragma unroll
-            for (int i = 0; i < MM; ++i)
-                if (has(i, j)) sp += L.P[i];
+            for (int i = 0; i < MM; ++i) {
+                if (kFast) sp = fmaf(L.h[i][j], L.P[i], sp);
+                else if (has(i, j)) sp += L.P[i];
+            }
             S[j] = sp;
             koff[j] = (n >= 2.0f) ? L.k_off2 : L.k_off1;
             kfree[j] = L.k_on * (2.0f - n);
-            c = fmaf(kfree[j], sp, c);       cum[6 * j + 4] = c;
-            c = fmaf(koff[j], n, c);         cum[6 * j + 5] = c;
+            c = fmaf(kfree[j], sp, c);       lc[6 * j + 4] = c;
+            c = fmaf(koff[j], n, c);         lc[6 * j + 5] = c;
+            g[j] = c;
         }
     }
-    const float a0 = c;
+    float a0 = g[0];
+#pragma unroll
+    for (int j = 1; j < MM; ++j) a0 += g[j];
 
     // ---- time to next event; grid samples crossed keep the pre-event state ----
     const float tau = (-0.69314718056f * fast_log2(u01(w_tau))) * fast_rcp(a0);   // a0 == 0 -> +inf
@@ -275,31 +297,36 @@ __device__ __forceinline__ void ssa_step(Lane<MM>& L, bool& active, bool& finish
     }
 
     // ---- select and fire (a lane that has just finished fires nothing: target beyond every sum) ----
-    const float target = alive ? u01(w_sel) * a0 : 3.0e38f;
+    float t = alive ? u01(w_sel) * a0 : 3.0e38f;
     float s_prev = 0.0f;
 #pragma unroll
     for (int j = 0; j < MM; ++j) {
         float d = 0.0f, d_b = 0.0f;
         if (j < nsp) {
-            const float s_tx = (target < cum[6 * j + 0]) ? 1.0f : 0.0f;
-            const float s_rm = (target < cum[6 * j + 1]) ? 1.0f : 0.0f;
-            const float s_tl = (target < cum[6 * j + 2]) ? 1.0f : 0.0f;
-            const float s_dp = (target < cum[6 * j + 3]) ? 1.0f : 0.0f;
-            const float s_b = (target < cum[6 * j + 4]) ? 1.0f : 0.0f;
-            const float s_u = (target < cum[6 * j + 5]) ? 1.0f : 0.0f;
+            const float s_tx = (t < lc[6 * j + 0]) ? 1.0f : 0.0f;
+            const float s_rm = (t < lc[6 * j + 1]) ? 1.0f : 0.0f;
+            const float s_tl = (t < lc[6 * j + 2]) ? 1.0f : 0.0f;
+            const float s_dp = (t < lc[6 * j + 3]) ? 1.0f : 0.0f;
+            const float s_b = (t < lc[6 * j + 4]) ? 1.0f : 0.0f;
+            const float s_u = (t < lc[6 * j + 5]) ? 1.0f : 0.0f;
             L.R[j] += fmaf(2.0f, s_tx, -s_prev) - s_rm;
             L.P[j] += fmaf(2.0f, s_tl, -s_rm) - s_dp;
             d_b = s_b - s_dp;                        // 1 if some regulator binds at j
             d = fmaf(2.0f, s_b, -s_dp) - s_u;        // +1 bind, -1 unbind, 0 neither
             s_prev = s_u;
         }
-        // Resolve which regulator (un)binds.  Warp-uniform vote: the hot loop is convergent here.
-        if (__any_sync(kFull, d != 0.0f)) {
+        if (kFast) {
+            // the one regulator of gene j (if any) is the one that (un)binds
+            L.n[j] += d;
+#pragma unroll
+            for (int i = 0; i < MM; ++i) L.P[i] = fmaf(-L.h[i][j], d, L.P[i]);
+        } else if (__any_sync(kFull, d != 0.0f)) {
+            // Resolve which regulator (un)binds.  Warp-uniform vote: the hot loop is convergent here.
             const bool bind = d_b != 0.0f;
-            const float base = bind ? cum[6 * j + 3] : cum[6 * j + 4];
+            const float base = bind ? lc[6 * j + 3] : lc[6 * j + 4];
             const float scale = bind ? kfree[j] : koff[j];
             const float tot = bind ? S[j] : L.n[j];                  // molecules in the lump (>= 1 if it fired)
-            float y = (target - base) * fast_rcp(scale);             // position inside the lump, in molecules
+            float y = (t - base) * fast_rcp(scale);                  // position inside the lump, in molecules
             y = fminf(y, __uint_as_float(__float_as_uint(tot) - 1u)); // strictly below the total: one regulator fires
             if (d == 0.0f) y = 3.0e38f;                              // lanes that fired nothing here
             float acc = 0.0f, sq = 0.0f;
@@ -317,6 +344,7 @@ __device__ __forceinline__ void ssa_step(Lane<MM>& L, bool& active, bool& finish
             }
             L.n[j] += d;
         }
+        t -= g[j];
     }
     L.events += (was_active && alive) ? 1u : 0u;
     if (!alive) lane_park<MM>(L);   // zero rates and state (rare; after the last use of the state above)
@@ -426,6 +454,18 @@ __device__ __forceinline__ void lane_init(Lane<MM>& L, const LaunchArgs& A, cons
 #pragma unroll
         for (int i = 0; i < MM; ++i) L.b[i][j] = 0.0f;
     }
+    // kFast tables (dead code in the other variants: nothing reads them there)
+#pragma unroll
+    for (int j = 0; j < MM; ++j) {
+        bool act = false;
+#pragma unroll
+        for (int i = 0; i < MM; ++i) {
+            const uint32_t e = topo_edge(job.topo, i, j);
+            L.h[i][j] = e ? 1.0f : 0.0f;
+            act = act || e == 1u;
+        }
+        L.kmb[j] = act ? L.km1 : L.km2;
+    }
     L.t_rem = 0.0f;
     L.k = 0; L.kd = 0; L.dcount = A.decim;
     L.events = 0;
@@ -436,7 +476,8 @@ __device__ __forceinline__ void lane_init(Lane<MM>& L, const LaunchArgs& A, cons
 // topology waits until the warp has drained) -- best for big jobs.  kMixed = true: every lane carries
 // its own topology, tiles are handed out without draining -- best for MCTS batches of many small jobs.
 // Results are identical in both modes.
-template <int MM, bool kMixed, bool kAllSpecies>
+// kFast: every job's topology gives each gene at most one regulator (requires !kMixed && kAllSpecies).
+template <int MM, bool kMixed, bool kAllSpecies, bool kFast = false>
 __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa_pairwise_kernel(const LaunchArgs A)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -446,8 +487,13 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa
     uint8_t* warp_ser = smem + (size_t)(warp * 32) * (MM * kSerStride);
     float* z = reinterpret_cast<float*>(smem + (size_t)kThreads * (MM * kSerStride)) + warp * kSerStride;
 
+    static_assert(!kFast || (!kMixed && kAllSpecies), "kFast needs one full-size topology per warp");
     Lane<MM> L;
     lane_park<MM>(L);
+#pragma unroll
+    for (int j = 0; j < MM; ++j)
+#pragma unroll
+        for (int i = 0; i < MM; ++i) L.h[i][j] = 0.0f;
     L.k = 0; L.kd = 0; L.dcount = 1; L.events = 0; L.ctr = 0; L.traj_lo = L.traj_hi = 0; L.out = 0;
     bool active = false, finished = false;
     // topology as two 25-bit masks + species count in bits 28..31 of `pres`
@@ -570,12 +616,13 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa
         L.ctr += 1;
         // A warp-wide OR of identical values: the result is warp-uniform by construction, which lets
         // the compiler keep the topology in uniform registers and branch uniformly on its bits.
-        const uint32_t u_pres = kMixed ? pres : __reduce_or_sync(kFull, pres);
-        const uint32_t u_act = kMixed ? actm : __reduce_or_sync(kFull, actm);
+        // (kFast reads the per-lane 0/1 edge matrix instead: no topology bits in its hot loop)
+        const uint32_t u_pres = (kMixed || kFast) ? pres : __reduce_or_sync(kFull, pres);
+        const uint32_t u_act = (kMixed || kFast) ? actm : __reduce_or_sync(kFull, actm);
         const int u_nsp = (int)(u_pres >> 28);
 #pragma unroll 1
         for (int h = 0; h < 2; ++h)
-            ssa_step<MM, kAllSpecies>(L, active, finished, u_pres, u_act, u_nsp, h ? x.w[2] : x.w[0], h ? x.w[3] : x.w[1],
+            ssa_step<MM, kAllSpecies, kFast>(L, active, finished, u_pres, u_act, u_nsp, h ? x.w[2] : x.w[0], h ? x.w[3] : x.w[1],
                                       ser, A.nt, A.decim, A.dt);
     }
     if (A.warp_iters && lane == 0) atomicAdd(A.warp_iters, n_iters);

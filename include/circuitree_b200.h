@@ -45,6 +45,8 @@ typedef struct ct_sim_config {
                                 (many small jobs).  Results are identical, only the speed differs. */
     int32_t lpt;             /* 1 (default): start trajectories longest-expected-first (cost pre-pass +
                                 radix sort); 0: in id order.  Results are identical. */
+    int32_t fast_path;       /* 1 (default): launches whose topologies give every gene at most one regulator
+                                use the specialised hot loop; 0: always the general one.  Results are identical. */
     float ranges[CT_MAX_PARAMS][3]; /* (lo, hi, is_log) per parameter, SPEC.md sections 4 and 9
                                 (rows 10, 11 = k_dim, k_undim are used by dimer topologies only) */
 } ct_sim_config;

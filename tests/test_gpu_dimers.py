@@ -18,8 +18,20 @@ if not torch.cuda.is_available():
 
 from scipy import stats
 
+from pathlib import Path
+
 from circuitree_b200 import DimersGrammar, OscillationTree, _capi
 from oracle import ssa_oracle as so
+
+# per-trajectory results of the CPU checker for the cases below, recorded by
+# tests/golden/make_dimer_oracle.py (minutes of CPU time; tests/test_oracle.py re-checks slices of them)
+GOLDEN = np.load(Path(__file__).parent / "golden" / "dimer_oracle.npz")
+
+
+def recorded(name):
+    return {"reward": GOLDEN[name + "/reward"], "lag": GOLDEN[name + "/lag"].astype(np.int64),
+            "n_events": GOLDEN[name + "/n_events"].astype(np.int64)}
+
 
 AI = ["activates", "inhibits"]
 THREADS = so.max_threads()
@@ -117,17 +129,20 @@ TOPOLOGIES = [
     "*ABC+R::",                          # no interactions
     "*ABC+R::ABiA_ABiB_CRaC_CCiA",       # shared heterodimer on two promoters, two interactions on promoter A
 ]
+CASE_NAMES = ["homodimer_repressilator", "heterodimer_regulator", "no_interactions", "shared_heterodimer"]
 
 
-@pytest.mark.parametrize("state", TOPOLOGIES)
-def test_statistical_equivalence(eng, cfg, state):
+@pytest.mark.parametrize("case", range(4))
+def test_statistical_equivalence(eng, cfg, case):
     # the bar's 10^4 trajectories at the full grid for the oscillator; the others (1.7e6 events per
-    # trajectory: the checker needs minutes) at 2500 trajectories on a 800-point grid
-    n = 10_000 if state == TOPOLOGIES[0] else 2500
-    if state != TOPOLOGIES[0]:
+    # trajectory) at 2500 trajectories on a 800-point grid.  Checker side: recorded, seed 202.
+    state = TOPOLOGIES[case]
+    n = 10_000 if case == 0 else 2500
+    if case != 0:
         cfg = small_cfg(nt=800, decim=16)
     g = gpu_run(eng, [state], n, cfg, seed=101)
-    o = oracle_run(state, n, cfg, seed=202)        # independent streams: a real two-sample test
+    o = recorded(CASE_NAMES[case])                 # independent streams: a real two-sample test
+    assert len(o["reward"]) == n
     se = np.sqrt(g["reward"].var(ddof=1) / n + o["reward"].var(ddof=1) / n)
     z = (g["reward"].mean() - o["reward"].mean()) / se
     assert abs(z) < 3.0, f"{state}: mean reward {g['reward'].mean():.4f} vs {o['reward'].mean():.4f} (z={z:.2f})"
@@ -145,7 +160,7 @@ def test_five_component_dimer_network(eng, cfg):
     n = 1000
     cfg = small_cfg(nt=800, decim=16)
     g = gpu_run(eng, [state], n, cfg, seed=31, grammar=g5)
-    o = oracle_run(state, n, cfg, seed=32, grammar=g5)
+    o = recorded("five_tf_ten_interactions")       # checker seed 32
     se = np.sqrt(g["reward"].var(ddof=1) / n + o["reward"].var(ddof=1) / n)
     assert abs(g["reward"].mean() - o["reward"].mean()) < 3.0 * se
     se_ev = np.sqrt(g["events"].var(ddof=1) / n + o["n_events"].astype(float).var(ddof=1) / n)
@@ -155,7 +170,7 @@ def test_five_component_dimer_network(eng, cfg):
 def test_same_stream_trajectories_track_the_checker(eng, cfg):
     n = 1000
     g = gpu_run(eng, [TOPOLOGIES[0]], n, cfg, seed=9)
-    o = oracle_run(TOPOLOGIES[0], n, cfg, seed=9)
+    o = recorded("same_stream")                    # checker seed 9: same parameters and initial conditions
     assert np.corrcoef(g["events"], o["n_events"].astype(float))[0, 1] > 0.99
 
 

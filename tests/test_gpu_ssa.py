@@ -219,6 +219,26 @@ def test_schedules_give_identical_results(eng):
         eng.rewards_host([handle_of("*AB::ABi")], [4], [0], bad, 1)
 
 
+def test_single_regulator_fast_path_is_bit_identical(eng):
+    """Launches whose topologies give every gene at most one regulator run a specialised hot loop
+    (ct_sim_config.fast_path); it must reproduce the general loop bit for bit."""
+    cases = [["*ABC::ABi_BCi_CAi"], ["*ABC::AAi_BAa_CBi", "*ABC::", "*ABC::CAa"], ["*ABCD::ABi_BCi_CDi_DAa"],
+             ["*ABCDE::ABi_BCa_CDi_DEi_EAi", "*ABCDE::AAa_EBi"]]
+    for states in cases:
+        outs = []
+        for fast in (1, 0):
+            c = small_cfg(nt=640, decim=16)
+            c.fast_path, c.schedule = fast, 1
+            outs.append(gpu_run(eng, states, 3000, c, seed=17))
+        c = small_cfg(nt=640, decim=16)
+        c.schedule = 2                                  # mixed lanes: always the general loop
+        outs.append(gpu_run(eng, states, 3000, c, seed=17))
+        for k in ("reward", "lag", "events"):
+            assert np.array_equal(outs[0][k], outs[1][k]), (states, k)
+            assert np.array_equal(outs[0][k], outs[2][k]), (states, k)
+        assert outs[0]["events"].sum() > 0
+
+
 def test_empty_and_ragged_jobs(eng):
     c = small_cfg(nt=160, decim=16)
     out = eng.rewards_host([handle_of("*AB::ABi"), handle_of("*AB::ABa"), handle_of("*AB::ABi")], [0, 3, 0], [0, 0, 0], c, 1,

@@ -152,3 +152,21 @@ def test_dimer_checker_rejects_bad_topologies():
         so.run_dimers(3, 3, [(1, 0, 2)], [], DIMER_RANGES, 1)      # monomers not sorted
     with pytest.raises(ValueError):
         so.run_dimers(3, 2, [(0, 1, 2)], [], DIMER_RANGES, 1)      # target is not a component
+
+
+def test_recorded_dimer_results_are_what_the_checker_computes():
+    """tests/golden/dimer_oracle.npz (used by the GPU parity tests) against a fresh run of a slice."""
+    import importlib.util
+    from pathlib import Path
+
+    here = Path(__file__).parent / "golden"
+    spec = importlib.util.spec_from_file_location("make_dimer_oracle", here / "make_dimer_oracle.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gold = np.load(here / "dimer_oracle.npz")
+    for name, case in mod.CASES.items():
+        assert len(gold[name + "/reward"]) == case[2]
+        r = mod.run_case(name, n=12, n_threads=4)
+        assert np.array_equal(r["reward"], gold[name + "/reward"][:12]), name
+        assert np.array_equal(r["lag"], gold[name + "/lag"][:12]), name
+        assert np.array_equal(r["n_events"], gold[name + "/n_events"][:12]), name
