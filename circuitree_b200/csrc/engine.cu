@@ -167,8 +167,10 @@ int ct_engine_create(int device, ct_engine** out)
     if ((rc = prepare_kernel<4, false, true, true>(eng->ki_fast[1])) != CT_OK) { delete eng; return rc; }
     if ((rc = prepare_kernel<5, false, true, true>(eng->ki_fast[2])) != CT_OK) { delete eng; return rc; }
     {
+        // the dimer kernel sizes its shared memory per launch (DimerLayout); allow the maximum here
         KernelInfo& ki = eng->ki_dimers;
-        ki.smem = (size_t)ct::kDimThreads * ct::kMaxSpecies * ct::kSerStride;
+        ct::DimerLayout lay{ct::kMaxSpecies, ct::kMaxEntries + 1};
+        ki.smem = lay.warp_bytes() * (ct::kDimThreads / 32);
         cudaError_t e1 = cudaFuncSetAttribute(ct::ssa_dimers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem);
         cudaError_t e2 = cudaFuncSetAttribute(ct::ssa_dimers_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                               cudaSharedmemCarveoutMaxShared);
@@ -310,15 +312,19 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
     CT_CUDA(cudaSetDevice(eng->device));
 
     const bool dimers = is_dimer_handle(handles[0]);
-    std::vector<ct::DimerTopo> topos;
+    std::vector<ct::DimerProg> progs;   // one reaction program per job (dimer model)
+    ct::DimerLayout lay{1, 1};
     if (dimers) {
-        topos.resize((size_t)n_jobs);
+        progs.resize((size_t)n_jobs);
         std::lock_guard<std::mutex> lock(g_dimer_mutex);
         for (int j = 0; j < n_jobs; ++j) {
             const uint64_t idx = handles[j] & 0xffffffffull;
             if (!is_dimer_handle(handles[j]) || idx >= g_dimer_topos.size())
                 return fail(CT_ERR_INVALID, "job %d: not a dimer topology handle (a launch takes one model only)", j);
-            topos[j] = g_dimer_topos[idx];
+            progs[j] = ct::dimer_program(g_dimer_topos[idx]);
+            if (n_traj[j] == 0) continue;
+            if (progs[j].n_tf > lay.ser_species) lay.ser_species = progs[j].n_tf;
+            if (progs[j].n_entries + 1 > lay.cum_slots) lay.cum_slots = progs[j].n_entries + 1;
         }
     }
     std::vector<ct::Job> jobs((size_t)n_jobs);
@@ -388,7 +394,7 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
     // schedule: big jobs -> one topology per warp (uniform branches); many small jobs -> mixed lanes
     bool mixed = cfg->schedule == 2;
     if (cfg->schedule == 0) mixed = n_jobs > 1 && total / (uint64_t)n_jobs < 2048;
-    if (dimers) mixed = true;   // the dimer kernel's lanes are independent: order by cost across jobs
+    if (dimers) mixed = false;  // the dimer kernel runs one topology per warp
     if (mixed) A.n_tiles = (uint32_t)((total + ct::kTile - 1) / ct::kTile);   // tiles over launch positions
 
     // longest-expected-first order (cfg->lpt): cost pre-pass + radix sort of (job, cost) keys
@@ -419,17 +425,20 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
         A.order = d_order;
     }
     if (dimers) {
-        ct::DimerTopo* d_topos = nullptr;
-        CT_CUDA(cudaMallocAsync((void**)&d_topos, sizeof(ct::DimerTopo) * topos.size(), stream));
-        CT_CUDA(cudaMemcpyAsync(d_topos, topos.data(), sizeof(ct::DimerTopo) * topos.size(), cudaMemcpyHostToDevice, stream));
-        const KernelInfo& kd = eng->ki_dimers;
+        ct::DimerProg* d_progs = nullptr;
+        CT_CUDA(cudaMallocAsync((void**)&d_progs, sizeof(ct::DimerProg) * progs.size(), stream));
+        CT_CUDA(cudaMemcpyAsync(d_progs, progs.data(), sizeof(ct::DimerProg) * progs.size(), cudaMemcpyHostToDevice, stream));
+        const size_t smem = lay.warp_bytes() * (ct::kDimThreads / 32);
+        int per_sm = 0;
+        CT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ct::ssa_dimers_kernel, ct::kDimThreads, smem));
+        if (per_sm < 1) return fail(CT_ERR_CUDA, "dimer SSA kernel does not fit on an SM (%zu bytes of shared memory)", smem);
         const uint64_t want = (total + ct::kDimThreads - 1) / ct::kDimThreads;
-        const uint64_t cap = (uint64_t)eng->n_sm * kd.blocks_per_sm;
-        ct::ssa_dimers_kernel<<<(unsigned)(want < cap ? want : cap), ct::kDimThreads, kd.smem, stream>>>(A, d_topos);
+        const uint64_t cap = (uint64_t)eng->n_sm * per_sm;
+        ct::ssa_dimers_kernel<<<(unsigned)(want < cap ? want : cap), ct::kDimThreads, smem, stream>>>(A, d_progs, lay);
         CT_CUDA(cudaGetLastError());
         eng->launches += 1;
         // (pageable host memory: the copy above has been staged when cudaMemcpyAsync returns)
-        CT_CUDA(cudaFreeAsync(d_topos, stream));
+        CT_CUDA(cudaFreeAsync(d_progs, stream));
         CT_CUDA(cudaFreeAsync(d_jobs, stream));
         CT_CUDA(cudaFreeAsync(d_counter, stream));
         if (d_keys) {

@@ -1,19 +1,34 @@
 // Batched Gillespie SSA + oscillation reward for the dimer model (SPEC.md section 9), the
 // simulator behind get_reward for DimersGrammar states (reference circuitree/models.py:844-884 is
-// the topology input).  First, table-driven version: one trajectory per lane, lanes are
-// independent (grid-stride over launch positions, longest-expected-first when `order` is given),
-// per-lane state in registers / local memory with the topology table read through the read-only
-// cache, the per-trajectory record in shared memory, and the reward computed by the lane itself.
-// It shares Philox streams, parameter sampling, companding and reward definition with the pairwise
-// kernel; it does not share its lock-step scheduling (config 3 is not the headline path).
+// the topology input).
+//
+// Same execution model as the pairwise kernel (ssa_pairwise.cuh): one trajectory per lane, one
+// topology per warp at a time, all 32 lanes step in lock-step, persistent warps pull 32-trajectory
+// tiles off a global counter and refill lanes as trajectories end, the finished lane's record is
+// reduced to (reward, lag) by the whole warp.  What differs is where the state lives.  A dimer
+// network has up to 5 TFs, 10 interactions and 10 dimer species whose wiring is data, not code, so
+// the per-lane state vector, the running sum of propensities and the record sit in shared memory
+// as [slot][lane] float arrays (bank = lane: conflict-free for any slot, uniform or per-lane), and
+// the warp walks the job's reaction program with warp-uniform loops:
+//   pass 1  running sum in SPEC order: per TF (transcription, mRNA decay, translation, monomer
+//           decay, binding of each interaction at its promoter, unbinding of each), then per dimer
+//           (dimerisation, dissociation); every partial sum is stored;
+//   pass 2  each lane binary-searches its own target in the stored sums (same trip count for all
+//           lanes) and applies the stoichiometry word of the reaction it found: four
+//           (slot, +1/-1) fields, read-modify-write on its own column.
+// Nothing in the hot loop diverges except the rare grid-crossing block.
 #pragma once
+#include <string.h>
+
 #include "ssa_pairwise.cuh"
 
 namespace ct {
 
-constexpr int kMaxIxn = 10;
-constexpr int kDimThreads = 128;
+constexpr int kMaxIxn = 10;                 // interactions, and distinct dimers, per topology
+constexpr int kDimThreads = 64;             // 2 warps per CTA (shared memory per warp is what limits residency)
+constexpr int kMaxEntries = 4 * kMaxSpecies + 4 * kMaxIxn;   // reactions in the running sum
 
+// canonical description of a dimer topology (the key of the process-wide handle table)
 struct DimerTopo {                  // 56 bytes
     uint8_t n_tf, n_comp, n_ixn, n_dim;
     uint8_t dim_a[kMaxIxn], dim_b[kMaxIxn];
@@ -21,171 +36,319 @@ struct DimerTopo {                  // 56 bytes
     uint8_t pad[2];
 };
 
-// SPEC.md section 7 computed by one lane from its own record (rare: once per trajectory)
-__device__ __forceinline__ void lane_reward(const uint8_t* ser, int nsp, int n_dec, float& reward_out, int& lag_out)
+// state slots of one lane (floats holding exact small integers)
+enum : int { kSlotP = 0, kSlotR = 5, kSlotD = 10, kSlotB = 20, kSlotN = 30, kSlotA = 35, kSlotBlk = 40, kSlotDummy = 45, kSlots = 46 };
+
+// The job's reaction program, built on the host from a DimerTopo (dimer_program below).
+struct DimerProg {                  // one per job
+    uint8_t n_tf, n_ixn, n_dim, n_entries;
+    uint8_t ix_start[kMaxSpecies + 1];   // interactions sorted by target (stable): TF s owns x in [ix_start[s], ix_start[s+1])
+    uint8_t search_iters;                // ceil(log2(n_entries + 1))
+    uint8_t pad0;
+    uint8_t ix_dim[kMaxIxn];             // dimer of sorted interaction x
+    uint8_t pad1[2];
+    uint8_t dim_a[kMaxIxn], dim_b[kMaxIxn];
+    uint32_t stoich[kMaxEntries + 1];    // reaction -> 4 x (slot | code << 6), code 1 = +1, 2 = -1; entry n_entries = none
+};
+static_assert(sizeof(DimerProg) % 4 == 0, "DimerProg is copied word by word");
+
+inline DimerProg dimer_program(const DimerTopo& T)
 {
-    const int max_lag = n_dec >> 1;
-    float best = 0.0f;
-    int best_lag = 0;
-    for (int s = 0; s < nsp; ++s) {
-        const uint8_t* q = ser + s * kSerStride;
-        float sum = 0.0f;
-        for (int k = 0; k < n_dec; ++k) { const float v = (float)q[k]; sum += v * v; }
-        const float mu = sum / (float)n_dec;
-        float c0 = 0.0f;
-        for (int k = 0; k < n_dec; ++k) { const float v = (float)q[k]; const float d = v * v - mu; c0 += d * d; }
-        if (!(c0 > 0.0f)) continue;
-        const float inv = 1.0f / c0;
-        float r_prev2 = 0.0f, r_prev = 1.0f;    // r(l-2), r(l-1)
-        for (int l = 1; l <= max_lag; ++l) {
-            float acc = 0.0f;
-            for (int k = 0; k + l < n_dec; ++k) {
-                const float a = (float)q[k], b = (float)q[k + l];
-                acc += (a * a - mu) * (b * b - mu);
-            }
-            const float r = acc * inv;
-            // r_prev = r(l-1) is a local minimum if r(l-2) > r(l-1) < r(l); candidates are lags 1..max_lag-1
-            if (l >= 2 && r_prev < r_prev2 && r_prev < r && r_prev < best) { best = r_prev; best_lag = l - 1; }
-            r_prev2 = r_prev;
-            r_prev = r;
+    DimerProg G;
+    memset(&G, 0, sizeof G);
+    G.n_tf = T.n_tf; G.n_ixn = T.n_ixn; G.n_dim = T.n_dim;
+    int sorted[kMaxIxn], nx = 0;
+    for (int s = 0; s < T.n_tf; ++s) {
+        G.ix_start[s] = (uint8_t)nx;
+        for (int e = 0; e < T.n_ixn; ++e)
+            if (T.ix_tgt[e] == s) sorted[nx++] = e;
+    }
+    for (int s = T.n_tf; s <= kMaxSpecies; ++s) G.ix_start[s] = (uint8_t)nx;
+    for (int x = 0; x < nx; ++x) G.ix_dim[x] = T.ix_dim[sorted[x]];
+    for (int d = 0; d < T.n_dim; ++d) { G.dim_a[d] = T.dim_a[d]; G.dim_b[d] = T.dim_b[d]; }
+    const uint32_t none = (uint32_t)kSlotDummy;
+    auto word = [&](uint32_t f0, uint32_t f1 = kSlotDummy, uint32_t f2 = kSlotDummy, uint32_t f3 = kSlotDummy) {
+        return f0 | (f1 << 8) | (f2 << 16) | (f3 << 24);
+    };
+    auto inc = [](int slot) { return (uint32_t)slot | (1u << 6); };
+    auto dec = [](int slot) { return (uint32_t)slot | (2u << 6); };
+    int r = 0;
+    for (int s = 0; s < T.n_tf; ++s) {
+        G.stoich[r++] = word(inc(kSlotR + s));
+        G.stoich[r++] = word(dec(kSlotR + s));
+        G.stoich[r++] = word(inc(kSlotP + s));
+        G.stoich[r++] = word(dec(kSlotP + s));
+        for (int x = G.ix_start[s]; x < G.ix_start[s + 1]; ++x) {
+            const bool act = T.ix_act[sorted[x]] != 0;
+            G.stoich[r++] = word(dec(kSlotD + G.ix_dim[x]), inc(kSlotB + x), inc(kSlotN + s), act ? inc(kSlotA + s) : none);
+        }
+        for (int x = G.ix_start[s]; x < G.ix_start[s + 1]; ++x) {
+            const bool act = T.ix_act[sorted[x]] != 0;
+            G.stoich[r++] = word(inc(kSlotD + G.ix_dim[x]), dec(kSlotB + x), dec(kSlotN + s), act ? dec(kSlotA + s) : none);
         }
     }
-    reward_out = fminf(fmaxf(-best, 0.0f), 1.0f);
-    lag_out = best_lag;
+    for (int d = 0; d < T.n_dim; ++d) {
+        G.stoich[r++] = word(dec(kSlotP + T.dim_a[d]), dec(kSlotP + T.dim_b[d]), inc(kSlotD + d));
+        G.stoich[r++] = word(inc(kSlotP + T.dim_a[d]), inc(kSlotP + T.dim_b[d]), dec(kSlotD + d));
+    }
+    G.n_entries = (uint8_t)r;
+    G.stoich[r] = word(none);
+    int it = 0;
+    while ((1 << it) < r + 1) ++it;
+    G.search_iters = (uint8_t)it;
+    return G;
 }
 
-__global__ void __launch_bounds__(kDimThreads) ssa_dimers_kernel(const LaunchArgs A, const DimerTopo* __restrict__ topos)
+// shared memory of one warp, sized per launch: record | state | running sums | reward scratch | program
+struct DimerLayout {
+    int32_t ser_species;      // species rows in the per-lane record (max n_tf of the launch)
+    int32_t cum_slots;        // max n_entries of the launch + 1 (the +inf sentinel)
+    __host__ __device__ size_t ser_bytes() const { return (size_t)32 * ser_species * kSerStride; }
+    __host__ __device__ size_t warp_bytes() const
+    {
+        return ser_bytes() + (size_t)(kSlots + cum_slots) * 32 * sizeof(float) + kSerStride * sizeof(float) + sizeof(DimerProg);
+    }
+};
+
+__global__ void __launch_bounds__(kDimThreads) ssa_dimers_kernel(const LaunchArgs A, const DimerProg* __restrict__ progs,
+                                                                 const DimerLayout lay)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t* ser = smem + (size_t)threadIdx.x * (kMaxSpecies * kSerStride);
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < A.total; pos += stride) {
-        const uint32_t slot = A.order ? A.order[pos] : pos;
-        const uint32_t jx = job_of_slot(A, slot);
-        const Job job = A.jobs[jx];
-        const DimerTopo T = topos[jx];            // per-launch table, one entry per job
-        const uint64_t traj = job.traj_base + (slot - job.out_offset);
-        const uint32_t t_lo = (uint32_t)traj, t_hi = (uint32_t)(traj >> 32);
-        float p[12];
-        trajectory_params(A, t_lo, t_hi, slot, p);
-        const float k_on = p[0], k_off1 = p[1], k_off2 = p[2], kp = p[7], gm = p[8], gp = p[9], k_dim = p[10], k_undim = p[11];
-        const float km[4] = {p[3], p[4], p[5], p[6]};
-        const int M = T.n_tf;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint8_t* wbase = smem + (size_t)warp * lay.warp_bytes();
+    uint8_t* warp_ser = wbase;
+    const int ser_lane_bytes = lay.ser_species * kSerStride;
+    uint8_t* ser = warp_ser + (size_t)lane * ser_lane_bytes;
+    float* X = reinterpret_cast<float*>(wbase + lay.ser_bytes()) + lane;     // slot s of this lane: X[s * 32]
+    float* cum = X + kSlots * 32;                                            // partial sum r of this lane: cum[r * 32]
+    float* z = reinterpret_cast<float*>(wbase + lay.ser_bytes()) + (kSlots + lay.cum_slots) * 32;
+    DimerProg* G = reinterpret_cast<DimerProg*>(z + kSerStride);
 
-        float P[kMaxSpecies], R[kMaxSpecies], blk[kMaxSpecies], D[kMaxIxn], b[kMaxIxn];
-        {
-            const float e0 = expf(-A.init_mean);
-            for (int blk4 = 0; blk4 < 2; ++blk4) {
-                const Philox4 x = philox4x32_10(3 + blk4, 0u, t_lo, t_hi, A.seed_lo, A.seed_hi);
-                for (int w = 0; w < 4; ++w) {
-                    const int s = 4 * blk4 + w;
-                    if (s < kMaxSpecies) {
-                        const float u = u01(x.w[w]);
-                        float pk = e0, F = e0;
-                        int kk = 0;
-                        while (u > F && kk < 1000) { ++kk; pk *= A.init_mean / (float)kk; F += pk; }
-                        P[s] = (s < M) ? (float)kk : 0.0f;
-                        R[s] = 0.0f;
-                        blk[s] = 0.0f;
-                    }
+    // per-lane rate constants (zero = parked lane: nothing fires)
+    float k_on = 0.f, k_off1 = 0.f, k_off2 = 0.f, km0 = 0.f, km1 = 0.f, km2 = 0.f, km3 = 0.f, kp = 0.f, gm = 0.f, gp = 0.f,
+          k_dim = 0.f, k_undim = 0.f;
+    float t_rem = 0.0f;
+    int k = 0, kd = 0, dcount = 1;
+    uint32_t events = 0, ctr = 0, traj_lo = 0, traj_hi = 0, out = 0;
+    bool active = false, finished = false;
+#pragma unroll 1
+    for (int s = 0; s < kSlots; ++s) X[s * 32] = 0.0f;
+
+    // warp-uniform tile state (same protocol as ssa_pairwise_kernel, one topology per warp)
+    Job job;
+    job.topo = ~0ull; job.traj_base = 0; job.n_traj = 0; job.out_offset = 0; job.tile_start = 0; job.pad = 0;
+    Job pend = job;
+    uint32_t pos = 0, end = 0, pend_pos = 0, pend_end = 0, pend_job = 0;
+    bool have_pending = false, out_of_work = false;
+    int n_tf = 0, n_dim = 0, n_entries = 0, search_iters = 0;
+    uint32_t n_iters = 0;
+
+    for (;;) {
+        const unsigned idle = __ballot_sync(kFull, !active);
+        if (idle) {
+            // 1. reduce finished trajectories to (reward, lag), one lane at a time, whole warp helping
+            unsigned fin = __ballot_sync(kFull, finished);
+            while (fin) {
+                const int src = __ffs(fin) - 1;
+                fin &= fin - 1;
+                float rw; int lg;
+                const uint8_t* sser = warp_ser + (size_t)src * ser_lane_bytes;
+                warp_reward(sser, z, n_tf, A.n_dec, lane, rw, lg);
+                const uint32_t o = __shfl_sync(kFull, out, src);
+                if (A.series) {
+                    for (int s = 0; s < n_tf; ++s)
+                        for (int q = lane; q < A.n_dec; q += 32)
+                            A.series[(size_t)o * A.series_stride + s * A.n_dec + q] = sser[s * kSerStride + q];
+                }
+                if (lane == src) {
+                    A.reward[o] = rw;
+                    if (A.lag) A.lag[o] = lg;
+                    if (A.events) A.events[o] = events;
+                    finished = false;
                 }
             }
-            for (int e = 0; e < kMaxIxn; ++e) { D[e] = 0.0f; b[e] = 0.0f; }
-        }
-        float t_rem = 0.0f;
-        int k = 0, kd = 0, dcount = A.decim;
-        uint32_t events = 0, ctr = 0;
-        bool done = false;
-        while (!done) {
-            const Philox4 x = philox4x32_10_rk(ctr++, 1u, t_lo, t_hi, A.rk);
-            for (int h = 0; h < 2 && !done; ++h) {
-                // ---- propensities, flat running sum in SPEC order ----
-                float cum[4 * kMaxSpecies + 4 * kMaxIxn];
-                int nr = 0;
-                float c = 0.0f;
-                for (int s = 0; s < M; ++s) {
-                    float n = 0.0f, na = 0.0f;
-                    for (int e = 0; e < T.n_ixn; ++e)
-                        if (T.ix_tgt[e] == s) { n += b[e]; if (T.ix_act[e]) na += b[e]; }
-                    const int sel = (na > 0.0f ? 1 : 0) | (n > na ? 2 : 0);
-                    c += (s < T.n_comp) ? km[sel] : km[0];  cum[nr++] = c;
-                    c = fmaf(gm, R[s], c);                  cum[nr++] = c;
-                    c = fmaf(kp, R[s], c);                  cum[nr++] = c;
-                    c = fmaf(gp, P[s], c);                  cum[nr++] = c;
-                    if (s < T.n_comp) {
-                        const float koff = (n >= 2.0f) ? k_off2 : k_off1;
-                        const float kfree = k_on * (2.0f - n);
-                        for (int e = 0; e < T.n_ixn; ++e)
-                            if (T.ix_tgt[e] == s) { c = fmaf(kfree, D[T.ix_dim[e]], c); cum[nr++] = c; }
-                        for (int e = 0; e < T.n_ixn; ++e)
-                            if (T.ix_tgt[e] == s) { c = fmaf(koff, b[e], c); cum[nr++] = c; }
+            // 2. hand out trajectories of the current tile; draw new tiles as needed
+            unsigned need = idle;
+            for (;;) {
+                if (pos < end) {
+                    const int rank = __popc(need & ((1u << lane) - 1u));
+                    const uint32_t avail = end - pos;
+                    const bool take = !active && (uint32_t)rank < avail;
+                    if (take) {
+                        const uint32_t p = job.out_offset + pos + rank;
+                        const uint32_t slot = A.order ? A.order[p] : p;
+                        const uint64_t traj = job.traj_base + (slot - job.out_offset);
+                        traj_lo = (uint32_t)traj; traj_hi = (uint32_t)(traj >> 32);
+                        out = slot;
+                        float prm[12];
+                        trajectory_params(A, traj_lo, traj_hi, slot, prm);
+                        k_on = prm[0]; k_off1 = prm[1]; k_off2 = prm[2]; km0 = prm[3]; km1 = prm[4]; km2 = prm[5]; km3 = prm[6];
+                        kp = prm[7]; gm = prm[8]; gp = prm[9]; k_dim = prm[10]; k_undim = prm[11];
+#pragma unroll 1
+                        for (int s = 0; s < kSlots; ++s) X[s * 32] = 0.0f;
+                        const float e0 = expf(-A.init_mean);
+#pragma unroll 1
+                        for (int blk4 = 0; blk4 < 2; ++blk4) {
+                            const Philox4 x = philox4x32_10(3 + blk4, 0u, traj_lo, traj_hi, A.seed_lo, A.seed_hi);
+#pragma unroll
+                            for (int w = 0; w < 4; ++w) {
+                                const int s = 4 * blk4 + w;
+                                if (s < n_tf) {
+                                    const float u = u01(x.w[w]);
+                                    float pk = e0, F = e0;
+                                    int kk = 0;
+                                    while (u > F && kk < 1000) { ++kk; pk *= A.init_mean / (float)kk; F += pk; }
+                                    X[(kSlotP + s) * 32] = (float)kk;
+                                }
+                            }
+                        }
+                        t_rem = 0.0f;
+                        k = 0; kd = 0; dcount = A.decim;
+                        events = 0; ctr = 0;
+                        active = true;
+                    }
+                    const uint32_t n_need = __popc(need);
+                    pos += (n_need < avail) ? n_need : avail;
+                    need = __ballot_sync(kFull, !active);
+                    if (!need) break;
+                }
+                if (!have_pending && !out_of_work) {
+                    uint32_t t = 0;
+                    if (lane == 0) t = atomicAdd(A.tile_counter, 1u);
+                    t = __shfl_sync(kFull, t, 0);
+                    if (t >= A.n_tiles) {
+                        out_of_work = true;
+                    } else {
+                        uint32_t lo = 0, hi = A.n_jobs - 1;       // last job with tile_start <= t
+                        while (lo < hi) {
+                            const uint32_t mid = (lo + hi + 1) >> 1;
+                            if (A.jobs[mid].tile_start <= t) lo = mid; else hi = mid - 1;
+                        }
+                        pend = A.jobs[lo];
+                        pend_job = lo;
+                        pend_pos = (t - pend.tile_start) * kTile;
+                        pend_end = min(pend_pos + (uint32_t)kTile, pend.n_traj);
+                        have_pending = true;
                     }
                 }
-                for (int d = 0; d < T.n_dim; ++d) {
-                    const int xa = T.dim_a[d], xb = T.dim_b[d];
-                    const float pairs = (xa != xb) ? P[xa] * P[xb] : 0.5f * P[xa] * (P[xa] - 1.0f);
-                    c = fmaf(k_dim, pairs, c);              cum[nr++] = c;
-                    c = fmaf(k_undim, D[d], c);             cum[nr++] = c;
+                if (have_pending) {
+                    const bool same = (pend.topo == job.topo);
+                    const bool drained = (__ballot_sync(kFull, active) == 0u);
+                    if (same || drained) {
+                        if (!same) {
+                            // switch topology: copy the job's program into the warp's shared memory
+                            const uint32_t* src = reinterpret_cast<const uint32_t*>(progs + pend_job);
+                            uint32_t* dst = reinterpret_cast<uint32_t*>(G);
+                            __syncwarp();
+                            for (int w = lane; w < (int)(sizeof(DimerProg) / 4); w += 32) dst[w] = src[w];
+                            __syncwarp();
+                            n_tf = G->n_tf; n_dim = G->n_dim; n_entries = G->n_entries; search_iters = G->search_iters;
+                            cum[n_entries * 32] = 3.4e38f;    // sentinel (every lane): "no reaction" is always found
+                        }
+                        job = pend; pos = pend_pos; end = pend_end;
+                        have_pending = false;
+                        continue;
+                    }
                 }
-                const float a0 = c;
-                const float tau = (-0.69314718056f * fast_log2(u01(h ? x.w[2] : x.w[0]))) * fast_rcp(a0);
-                t_rem -= tau;
-                while (t_rem < 0.0f && k < A.nt) {
-                    for (int s = 0; s < kMaxSpecies; ++s) blk[s] += fminf(P[s], kSampleCap);
-                    ++k;
+                break;   // wait for running lanes (or nothing left)
+            }
+            if (out_of_work && __ballot_sync(kFull, active) == 0u) break;
+        }
+        ++n_iters;
+
+        const Philox4 x = philox4x32_10_rk(ctr, 1u, traj_lo, traj_hi, A.rk);
+        ctr += 1;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t w_tau = h ? x.w[2] : x.w[0], w_sel = h ? x.w[3] : x.w[1];
+            // ---- pass 1: running sum of propensities in SPEC order, every partial sum stored ----
+            float c = 0.0f;
+            float* cp = cum;
+#pragma unroll 1
+            for (int s = 0; s < n_tf; ++s) {
+                const float n = X[(kSlotN + s) * 32], na = X[(kSlotA + s) * 32];
+                const float r = X[(kSlotR + s) * 32], p = X[(kSlotP + s) * 32];
+                const float km_a = (na > 0.0f) ? km1 : km0;
+                const float km_i = (na > 0.0f) ? km3 : km2;
+                c += (n > na) ? km_i : km_a;    cp[0] = c;
+                c = fmaf(gm, r, c);             cp[32] = c;
+                c = fmaf(kp, r, c);             cp[64] = c;
+                c = fmaf(gp, p, c);             cp[96] = c;
+                cp += 128;
+                const int x0 = G->ix_start[s], x1 = G->ix_start[s + 1];
+                if (x1 > x0) {
+                    const float kfree = k_on * (2.0f - n);
+                    const float koff = (n >= 2.0f) ? k_off2 : k_off1;
+#pragma unroll 1
+                    for (int q = x0; q < x1; ++q) { c = fmaf(kfree, X[(kSlotD + G->ix_dim[q]) * 32], c); *cp = c; cp += 32; }
+#pragma unroll 1
+                    for (int q = x0; q < x1; ++q) { c = fmaf(koff, X[(kSlotB + q) * 32], c); *cp = c; cp += 32; }
+                }
+            }
+#pragma unroll 1
+            for (int d = 0; d < n_dim; ++d) {
+                const int da = G->dim_a[d], db = G->dim_b[d];
+                const float pa = X[(kSlotP + da) * 32], pb = X[(kSlotP + db) * 32];
+                const float pairs = (da != db) ? pa * pb : 0.5f * pa * (pa - 1.0f);
+                c = fmaf(k_dim, pairs, c);                      cp[0] = c;
+                c = fmaf(k_undim, X[(kSlotD + d) * 32], c);     cp[32] = c;
+                cp += 64;
+            }
+            const float a0 = c;
+
+            // ---- time to next event; grid samples crossed keep the pre-event state ----
+            const float tau = (-0.69314718056f * fast_log2(u01(w_tau))) * fast_rcp(a0);   // a0 == 0 -> +inf
+            t_rem -= tau;
+            bool alive = true;
+            const bool was_active = active;
+            if (active && t_rem < 0.0f) {
+                do {
+#pragma unroll 1
+                    for (int s = 0; s < n_tf; ++s) X[(kSlotBlk + s) * 32] += fminf(X[(kSlotP + s) * 32], kSampleCap);
+                    k += 1;
                     if (--dcount == 0) {
                         dcount = A.decim;
-                        for (int s = 0; s < kMaxSpecies; ++s) {
-                            if (s < M) ser[s * kSerStride + kd] = (uint8_t)compand_block(blk[s]);
-                            blk[s] = 0.0f;
+#pragma unroll 1
+                        for (int s = 0; s < n_tf; ++s) {
+                            ser[s * kSerStride + kd] = (uint8_t)compand_block(X[(kSlotBlk + s) * 32]);
+                            X[(kSlotBlk + s) * 32] = 0.0f;
                         }
-                        ++kd;
+                        kd += 1;
                     }
                     t_rem += A.dt;
-                }
-                if (k >= A.nt) { done = true; break; }
-                // ---- select: first reaction whose running sum exceeds the target ----
-                const float target = u01(h ? x.w[3] : x.w[1]) * a0;
-                int sel = -1;
-                for (int r = 0; r < nr; ++r)
-                    if (target < cum[r]) { sel = r; break; }
-                ++events;
-                if (sel < 0) continue;          // rounding left none: the step fires nothing
-                // ---- apply (same walk as the propensity pass) ----
-                int r = 0;
-                bool applied = false;
-                for (int s = 0; s < M && !applied; ++s) {
-                    if (sel < r + 4) {
-                        const int w = sel - r;
-                        if (w == 0) R[s] += 1.0f; else if (w == 1) R[s] -= 1.0f; else if (w == 2) P[s] += 1.0f; else P[s] -= 1.0f;
-                        applied = true;
-                        break;
-                    }
-                    r += 4;
-                    if (s < T.n_comp) {
-                        for (int e = 0; e < T.n_ixn && !applied; ++e)
-                            if (T.ix_tgt[e] == s) { if (sel == r) { D[T.ix_dim[e]] -= 1.0f; b[e] += 1.0f; applied = true; } ++r; }
-                        for (int e = 0; e < T.n_ixn && !applied; ++e)
-                            if (T.ix_tgt[e] == s) { if (sel == r) { D[T.ix_dim[e]] += 1.0f; b[e] -= 1.0f; applied = true; } ++r; }
-                    }
-                }
-                for (int d = 0; d < T.n_dim && !applied; ++d) {
-                    const int xa = T.dim_a[d], xb = T.dim_b[d];
-                    if (sel == r) { P[xa] -= 1.0f; P[xb] -= 1.0f; D[d] += 1.0f; applied = true; }
-                    else if (sel == r + 1) { P[xa] += 1.0f; P[xb] += 1.0f; D[d] -= 1.0f; applied = true; }
-                    r += 2;
-                }
+                } while (t_rem < 0.0f && k < A.nt);
+                if (k >= A.nt) { alive = false; active = false; finished = true; }
+            }
+
+            // ---- pass 2: each lane finds its reaction (first partial sum above the target) and fires it ----
+            const float target = alive ? u01(w_sel) * a0 : 3.0e38f;
+            int lo = 0, hi = n_entries;
+#pragma unroll 1
+            for (int it = 0; it < search_iters; ++it) {
+                const int mid = (lo + hi) >> 1;
+                const bool lt = target < cum[mid * 32];
+                hi = lt ? mid : hi;
+                lo = lt ? lo : mid + 1;
+            }
+            uint32_t sw = G->stoich[lo];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                const uint32_t slot = sw & 63u, code = (sw >> 6) & 3u;
+                const float delta = (float)(int)(code & 1u) - (float)(int)(code >> 1);
+                X[slot * 32] += delta;
+                sw >>= 8;
+            }
+            events += (was_active && alive) ? 1u : 0u;
+            if (!alive) {   // park: zero rates and state so that the lane idles through the lock-step loop
+                k_on = k_off1 = k_off2 = km0 = km1 = km2 = km3 = kp = gm = gp = k_dim = k_undim = 0.0f;
+#pragma unroll 1
+                for (int s = 0; s < kSlots; ++s) X[s * 32] = 0.0f;
+                t_rem = 0.0f;
             }
         }
-        float rw; int lg;
-        lane_reward(ser, M, A.n_dec, rw, lg);
-        if (A.series)
-            for (int s = 0; s < M; ++s)
-                for (int q = 0; q < A.n_dec; ++q) A.series[(size_t)slot * A.series_stride + s * A.n_dec + q] = ser[s * kSerStride + q];
-        A.reward[slot] = rw;
-        if (A.lag) A.lag[slot] = lg;
-        if (A.events) A.events[slot] = events;
     }
+    if (A.warp_iters && lane == 0) atomicAdd(A.warp_iters, (unsigned long long)n_iters);
 }
 
 }  // namespace ct
