@@ -12,6 +12,17 @@
 
 #include "philox.cuh"
 
+// build-time variants of the hot loop (scripts/variants.sh times them side by side; results are identical)
+#ifndef CT_GRID_PRED
+#define CT_GRID_PRED 0        // 1: branch-free common case of the grid crossing
+#endif
+#ifndef CT_UNROLL_H
+#define CT_UNROLL_H 0         // 1: the two steps of a Philox block are unrolled into one basic block
+#endif
+#ifndef CT_PHILOX_AHEAD
+#define CT_PHILOX_AHEAD 0     // 1: the next Philox block is generated next to the current block's two steps
+#endif
+
 namespace ct {
 
 constexpr int kThreads = 128;        // 4 warps per CTA
@@ -156,11 +167,12 @@ struct Lane {
     float h[MM][MM];         // kFast only: 1.0f where edge i->j exists (each gene has at most one regulator)
     float kmb[MM];           // kFast only: transcription rate of gene j with its regulator bound (km_act or km_rep)
     float blk[MM];
-    float k_on, k_off1, k_off2, km0, km1, km2, km3, kp, gm, gp;
+    float k_on, k_on2, k_off1, k_off2, km0, km1, km2, km3, kp, gm, gp;   // k_on2 = 2 k_on
     float t_rem;
     int k, kd, dcount;
     uint32_t events;
     uint32_t ctr;           // next Philox block of stream 1
+    Philox4 x;              // CT_PHILOX_AHEAD: the block the next two steps will consume
     uint32_t traj_lo, traj_hi;
     uint32_t out;           // output slot
 };
@@ -188,7 +200,7 @@ __device__ __forceinline__ float compand_block(float s)
 template <int MM>
 __device__ __forceinline__ void lane_park(Lane<MM>& L)
 {
-    L.k_on = L.k_off1 = L.k_off2 = L.km0 = L.km1 = L.km2 = L.km3 = L.kp = L.gm = L.gp = 0.0f;
+    L.k_on = L.k_on2 = L.k_off1 = L.k_off2 = L.km0 = L.km1 = L.km2 = L.km3 = L.kp = L.gm = L.gp = 0.0f;
 #pragma unroll
     for (int j = 0; j < MM; ++j) {
         L.P[j] = L.R[j] = L.blk[j] = L.n[j] = L.A[j] = L.kmb[j] = 0.0f;
@@ -258,7 +270,7 @@ __device__ __forceinline__ void ssa_step(Lane<MM>& L, bool& active, bool& finish
             }
             S[j] = sp;
             koff[j] = (n >= 2.0f) ? L.k_off2 : L.k_off1;
-            kfree[j] = L.k_on * (2.0f - n);
+            kfree[j] = fmaf(-L.k_on, n, L.k_on2);    // k_on (2 - n), exact for n = 0, 1, 2
             c = fmaf(kfree[j], sp, c);       lc[6 * j + 4] = c;
             c = fmaf(koff[j], n, c);         lc[6 * j + 5] = c;
             g[j] = c;
@@ -273,6 +285,45 @@ __device__ __forceinline__ void ssa_step(Lane<MM>& L, bool& active, bool& finish
     L.t_rem -= tau;
     bool alive = true;     // no early return: every lane must reach the warp votes below
     const bool was_active = active;
+#if CT_GRID_PRED
+    // Grid crossing, common case branch-free: a warp has a crossing lane on ~40% of its steps (2000
+    // grid points per ~10^5 events, 32 lanes), so a divergent block here costs every warp; the first
+    // crossed sample is recorded with predicated adds and only a block boundary, a second crossing in
+    // the same step or the end of the grid (a few percent of warp-steps) takes the branch.
+    const bool cross = active && L.t_rem < 0.0f;
+#pragma unroll
+    for (int j = 0; j < MM; ++j) L.blk[j] += cross ? fminf(L.P[j], kSampleCap) : 0.0f;
+    L.k += cross ? 1 : 0;
+    L.dcount -= cross ? 1 : 0;
+    L.t_rem += cross ? dt : 0.0f;
+    const bool rare = cross && (L.dcount == 0 || L.t_rem < 0.0f || L.k >= nt);
+    if (__any_sync(kFull, rare)) {
+        if (rare) {
+            auto flush = [&]() {
+                L.dcount = decim;
+#pragma unroll
+                for (int j = 0; j < MM; ++j) {
+                    if (j < nsp) ser[j * kSerStride + L.kd] = (uint8_t)compand_block(L.blk[j]);
+                    L.blk[j] = 0.0f;
+                }
+                L.kd += 1;
+            };
+            if (L.dcount == 0) flush();
+            while (L.t_rem < 0.0f && L.k < nt) {
+#pragma unroll
+                for (int j = 0; j < MM; ++j) L.blk[j] += fminf(L.P[j], kSampleCap);
+                L.k += 1;
+                if (--L.dcount == 0) flush();
+                L.t_rem += dt;
+            }
+            if (L.k >= nt) {       // last grid sample recorded: the lane parks until the warp reduces its record
+                alive = false;
+                active = false;
+                finished = true;
+            }
+        }
+    }
+#else
     if (active && L.t_rem < 0.0f) {
         do {
 #pragma unroll
@@ -296,19 +347,27 @@ __device__ __forceinline__ void ssa_step(Lane<MM>& L, bool& active, bool& finish
         }
     }
 
+#endif
+
     // ---- select and fire (a lane that has just finished fires nothing: target beyond every sum) ----
+    // s_r = [t < lc_r] as a float comes from the FMA pipe: saturate((lc_r - t) * 2^60) is 1 when
+    // lc_r > t (the smallest positive difference of two such floats is far above 2^-60) and 0 when
+    // lc_r <= t; the scaling by a power of two is exact, so the sign is that of the exact difference.
+    // The compare/select pipe runs at half the FMA pipe's rate and is the busier one in this loop.
+    constexpr float kBig = 1152921504606846976.0f;   // 2^60
     float t = alive ? u01(w_sel) * a0 : 3.0e38f;
     float s_prev = 0.0f;
 #pragma unroll
     for (int j = 0; j < MM; ++j) {
         float d = 0.0f, d_b = 0.0f;
         if (j < nsp) {
-            const float s_tx = (t < lc[6 * j + 0]) ? 1.0f : 0.0f;
-            const float s_rm = (t < lc[6 * j + 1]) ? 1.0f : 0.0f;
-            const float s_tl = (t < lc[6 * j + 2]) ? 1.0f : 0.0f;
-            const float s_dp = (t < lc[6 * j + 3]) ? 1.0f : 0.0f;
-            const float s_b = (t < lc[6 * j + 4]) ? 1.0f : 0.0f;
-            const float s_u = (t < lc[6 * j + 5]) ? 1.0f : 0.0f;
+            const float tb = -t * kBig;             // (-inf for a finished lane: every s is 0)
+            const float s_tx = __saturatef(fmaf(lc[6 * j + 0], kBig, tb));
+            const float s_rm = __saturatef(fmaf(lc[6 * j + 1], kBig, tb));
+            const float s_tl = __saturatef(fmaf(lc[6 * j + 2], kBig, tb));
+            const float s_dp = __saturatef(fmaf(lc[6 * j + 3], kBig, tb));
+            const float s_b = __saturatef(fmaf(lc[6 * j + 4], kBig, tb));
+            const float s_u = __saturatef(fmaf(lc[6 * j + 5], kBig, tb));
             L.R[j] += fmaf(2.0f, s_tx, -s_prev) - s_rm;
             L.P[j] += fmaf(2.0f, s_tl, -s_rm) - s_dp;
             d_b = s_b - s_dp;                        // 1 if some regulator binds at j
@@ -425,7 +484,7 @@ __device__ __forceinline__ void lane_init(Lane<MM>& L, const LaunchArgs& A, cons
     L.out = job.out_offset + idx;
     float p[12];
     trajectory_params(A, L.traj_lo, L.traj_hi, L.out, p);
-    L.k_on = p[0]; L.k_off1 = p[1]; L.k_off2 = p[2];
+    L.k_on = p[0]; L.k_on2 = 2.0f * p[0]; L.k_off1 = p[1]; L.k_off2 = p[2];
     L.km0 = p[3]; L.km1 = p[4]; L.km2 = p[5]; L.km3 = p[6];
     L.kp = p[7]; L.gm = p[8]; L.gp = p[9];
 
@@ -470,6 +529,10 @@ __device__ __forceinline__ void lane_init(Lane<MM>& L, const LaunchArgs& A, cons
     L.k = 0; L.kd = 0; L.dcount = A.decim;
     L.events = 0;
     L.ctr = 0;
+#if CT_PHILOX_AHEAD
+    L.x = philox4x32_10_rk(0u, 1u, L.traj_lo, L.traj_hi, A.rk);
+    L.ctr = 1;
+#endif
 }
 
 // kMixed = false: a warp runs one topology at a time (uniform edge branches; a tile with another
@@ -495,6 +558,7 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa
 #pragma unroll
         for (int i = 0; i < MM; ++i) L.h[i][j] = 0.0f;
     L.k = 0; L.kd = 0; L.dcount = 1; L.events = 0; L.ctr = 0; L.traj_lo = L.traj_hi = 0; L.out = 0;
+    L.x.w[0] = L.x.w[1] = L.x.w[2] = L.x.w[3] = 0u;
     bool active = false, finished = false;
     // topology as two 25-bit masks + species count in bits 28..31 of `pres`
     // (uniform mode: the warp's topology; mixed mode: this lane's topology)
@@ -612,7 +676,12 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa
         ++n_iters;
 
         // two steps per Philox block (SPEC.md section 3); every lane runs them, parked lanes as no-ops
+#if CT_PHILOX_AHEAD
+        const Philox4 x = L.x;
+        const Philox4 x_next = philox4x32_10_rk(L.ctr, 1u, L.traj_lo, L.traj_hi, A.rk);   // independent of the steps below
+#else
         const Philox4 x = philox4x32_10_rk(L.ctr, 1u, L.traj_lo, L.traj_hi, A.rk);
+#endif
         L.ctr += 1;
         // A warp-wide OR of identical values: the result is warp-uniform by construction, which lets
         // the compiler keep the topology in uniform registers and branch uniformly on its bits.
@@ -620,10 +689,17 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa
         const uint32_t u_pres = (kMixed || kFast) ? pres : __reduce_or_sync(kFull, pres);
         const uint32_t u_act = (kMixed || kFast) ? actm : __reduce_or_sync(kFull, actm);
         const int u_nsp = (int)(u_pres >> 28);
+#if CT_UNROLL_H
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
         for (int h = 0; h < 2; ++h)
             ssa_step<MM, kAllSpecies, kFast>(L, active, finished, u_pres, u_act, u_nsp, h ? x.w[2] : x.w[0], h ? x.w[3] : x.w[1],
                                       ser, A.nt, A.decim, A.dt);
+#if CT_PHILOX_AHEAD
+        L.x = x_next;
+#endif
     }
     if (A.warp_iters && lane == 0) atomicAdd(A.warp_iters, n_iters);
 }
