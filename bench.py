@@ -30,6 +30,10 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 REPRESSILATOR = "*ABC::ABi_BCi_CAi"
+DIMER_REPRESSILATOR = "*ABC+::AAiB_BBiC_CCiA"
+# dram__bytes_read.sum + dram__bytes_write.sum of one ssa_pairwise_kernel<3,0,1,1> launch over 2^22 trajectories
+# (ncu, round 1: 44,168,960 + 26,891,520; profiles/r01b_dram_2p22.txt)
+DRAM_BYTES_PER_LAUNCH_2P22 = 71060480
 METRIC = "gillespie_reaction_steps_per_s"
 UNIT = "reaction-steps/s"
 # Algorithmic issue slots per SSA step for R reactions and M species (DESIGN.md "Roofline"):
@@ -149,6 +153,7 @@ def main() -> None:
     ap.add_argument("--mcts-batches", type=int, default=6)
     ap.add_argument("--mcts-depth", type=int, default=3, help="reward batches in flight (virtual loss)")
     ap.add_argument("--mcts-traj", type=int, default=16, help="SSA trajectories per rollout in the MCTS leg")
+    ap.add_argument("--dimer-log2-traj", type=int, default=15, help="trajectories of the dimer-model leg = 2^T (0 = skip)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -263,14 +268,29 @@ def main() -> None:
     mcts_events = tree.reward_engine.total_events - ev0
     mcts_launches = tree.reward_engine.engine.launch_count
 
+    # ---- dimer model (BASELINE config 3's kernel): homodimer repressilator through the same public API ----
+    dimer_secs, dimer_events, n_dimer = 1.0, 0, 0
+    if args.dimer_log2_traj > 0:
+        from circuitree_b200 import DimersGrammar
+
+        dgrammar = DimersGrammar(components=["A", "B", "C"], regulators=[], interactions=["activates", "inhibits"])
+        dre = RewardEngine(dgrammar, device=local_rank, seed=rank)
+        n_dimer = 1 << args.dimer_log2_traj
+        dre.run([DIMER_REPRESSILATOR], 2048)                                     # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        dimer_events = int(dre.run([DIMER_REPRESSILATOR], n_dimer)["job_events"].sum())
+        barrier()
+        dimer_secs = time.perf_counter() - t0
+
     # ---- reduce over ranks: max time, summed events ----
-    stats = torch.tensor([kernel_ms, e2e_secs, float(total_events), float(e2e_events), mcts_secs, float(mcts_events)],
-                         dtype=torch.float64, device=dev)
+    stats = torch.tensor([kernel_ms, e2e_secs, float(total_events), float(e2e_events), mcts_secs, float(mcts_events),
+                          dimer_secs, float(dimer_events)], dtype=torch.float64, device=dev)
     if world > 1:
         mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        kernel_ms, e2e_secs, mcts_secs = float(mx[0]), float(mx[1]), float(mx[4])
-        total_events, e2e_events, mcts_events = float(sm[2]), float(sm[3]), float(sm[5])
+        kernel_ms, e2e_secs, mcts_secs, dimer_secs = float(mx[0]), float(mx[1]), float(mx[4]), float(mx[6])
+        total_events, e2e_events, mcts_events, dimer_events = float(sm[2]), float(sm[3]), float(sm[5]), float(sm[7])
     value = total_events / (kernel_ms * 1e-3)
     e2e_value = e2e_events / e2e_secs
 
@@ -296,10 +316,11 @@ def main() -> None:
                     "steps": e2e_steps, "api": "RewardEngine.run -> ct_rewards_host (explicit host parameter vectors)"},
             "gpu_launches": int(launches),   # SSA kernel launches inside the timed region of `value`
             "roofline": {"bound": "alu_issue", "achieved": achieved, "peak": peak, "unit": "Tlane-instr/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": DRAM_BYTES_PER_LAUNCH_2P22 if args.log2_traj == 22 else None,
                          "note": f"algorithmic {i_step(n_react, n_spec):.1f} issue slots/step (DESIGN.md) x steps/s per GPU; "
-                                 f"peak = {n_sm} SMs x 128 lanes x {sm_max:.0f} MHz; HBM traffic per launch is "
-                                 f"~{(n * 12) / 1e6:.0f} MB of outputs (see profiles/)"},
+                                 f"peak = {n_sm} SMs x 128 lanes x {sm_max:.0f} MHz (issue bound: no HBM or tensor roofline applies); "
+                                 f"traffic = dram bytes read+written by one 2^22 launch (ncu, profiles/r01b_dram_2p22.txt) "
+                                 f"against {(n * 12) / 1e6:.0f} MB of outputs + {(n * 4) / 1e6:.0f} MB launch order"},
             "mean_reward": mean_reward, "wall_s_timed_region": wall,
             "mcts": {"metric": "mcts_rollouts_per_s", "value": world * mcts_K * mcts_batches / mcts_secs, "unit": "rollouts/s",
                      "reaction_steps_per_s": mcts_events / mcts_secs,
@@ -311,6 +332,11 @@ def main() -> None:
                                 "host_seconds_rank0": {k: round(v, 3) for k, v in tree.timing.items()},
                                 "merge_bytes_rank0": search.bytes_exchanged}},
         }
+        if n_dimer:
+            line["dimers"] = {"metric": METRIC, "value": dimer_events / dimer_secs, "unit": UNIT,
+                              "config": {"workload": f"dimer model (SPEC.md section 9), homodimer repressilator {DIMER_REPRESSILATOR}: "
+                                                     f"2^{args.dimer_log2_traj} trajectories x {cfg.nt} grid points per GPU, "
+                                                     "host API (RewardEngine.run), parameters sampled in-kernel"}}
         if not args.no_cpu_baseline:
             from oracle import ssa_oracle
 

@@ -12,15 +12,13 @@
 
 #include "philox.cuh"
 
-// build-time variants of the hot loop (scripts/variants.sh times them side by side; results are identical)
-#ifndef CT_GRID_PRED
-#define CT_GRID_PRED 0        // 1: branch-free common case of the grid crossing
-#endif
+// Build-time variant of the hot loop (scripts/build_variants.sh + scripts/variants.sh time variants
+// side by side on the GPU; results are identical).  Measured on B200 at 2^21 repressilator
+// trajectories: rolled 1.495e11 steps/s, unrolled 1.572e11.  Tried and dropped: a predicated
+// (branch-free) first grid crossing (-3 %), generating the next Philox block beside the current
+// block's steps (+-0 %).
 #ifndef CT_UNROLL_H
-#define CT_UNROLL_H 0         // 1: the two steps of a Philox block are unrolled into one basic block
-#endif
-#ifndef CT_PHILOX_AHEAD
-#define CT_PHILOX_AHEAD 0     // 1: the next Philox block is generated next to the current block's two steps
+#define CT_UNROLL_H 1         // 1: the two steps of a Philox block are unrolled into one basic block
 #endif
 
 namespace ct {
@@ -172,7 +170,6 @@ struct Lane {
     int k, kd, dcount;
     uint32_t events;
     uint32_t ctr;           // next Philox block of stream 1
-    Philox4 x;              // CT_PHILOX_AHEAD: the block the next two steps will consume
     uint32_t traj_lo, traj_hi;
     uint32_t out;           // output slot
 };
@@ -285,45 +282,6 @@ __device__ __forceinline__ void ssa_step(Lane<MM>& L, bool& active, bool& finish
     L.t_rem -= tau;
     bool alive = true;     // no early return: every lane must reach the warp votes below
     const bool was_active = active;
-#if CT_GRID_PRED
-    // Grid crossing, common case branch-free: a warp has a crossing lane on ~40% of its steps (2000
-    // grid points per ~10^5 events, 32 lanes), so a divergent block here costs every warp; the first
-    // crossed sample is recorded with predicated adds and only a block boundary, a second crossing in
-    // the same step or the end of the grid (a few percent of warp-steps) takes the branch.
-    const bool cross = active && L.t_rem < 0.0f;
-#pragma unroll
-    for (int j = 0; j < MM; ++j) L.blk[j] += cross ? fminf(L.P[j], kSampleCap) : 0.0f;
-    L.k += cross ? 1 : 0;
-    L.dcount -= cross ? 1 : 0;
-    L.t_rem += cross ? dt : 0.0f;
-    const bool rare = cross && (L.dcount == 0 || L.t_rem < 0.0f || L.k >= nt);
-    if (__any_sync(kFull, rare)) {
-        if (rare) {
-            auto flush = [&]() {
-                L.dcount = decim;
-#pragma unroll
-                for (int j = 0; j < MM; ++j) {
-                    if (j < nsp) ser[j * kSerStride + L.kd] = (uint8_t)compand_block(L.blk[j]);
-                    L.blk[j] = 0.0f;
-                }
-                L.kd += 1;
-            };
-            if (L.dcount == 0) flush();
-            while (L.t_rem < 0.0f && L.k < nt) {
-#pragma unroll
-                for (int j = 0; j < MM; ++j) L.blk[j] += fminf(L.P[j], kSampleCap);
-                L.k += 1;
-                if (--L.dcount == 0) flush();
-                L.t_rem += dt;
-            }
-            if (L.k >= nt) {       // last grid sample recorded: the lane parks until the warp reduces its record
-                alive = false;
-                active = false;
-                finished = true;
-            }
-        }
-    }
-#else
     if (active && L.t_rem < 0.0f) {
         do {
 #pragma unroll
@@ -347,7 +305,6 @@ __device__ __forceinline__ void ssa_step(Lane<MM>& L, bool& active, bool& finish
         }
     }
 
-#endif
 
     // ---- select and fire (a lane that has just finished fires nothing: target beyond every sum) ----
     // s_r = [t < lc_r] as a float comes from the FMA pipe: saturate((lc_r - t) * 2^60) is 1 when
@@ -529,10 +486,6 @@ __device__ __forceinline__ void lane_init(Lane<MM>& L, const LaunchArgs& A, cons
     L.k = 0; L.kd = 0; L.dcount = A.decim;
     L.events = 0;
     L.ctr = 0;
-#if CT_PHILOX_AHEAD
-    L.x = philox4x32_10_rk(0u, 1u, L.traj_lo, L.traj_hi, A.rk);
-    L.ctr = 1;
-#endif
 }
 
 // kMixed = false: a warp runs one topology at a time (uniform edge branches; a tile with another
@@ -558,7 +511,6 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa
 #pragma unroll
         for (int i = 0; i < MM; ++i) L.h[i][j] = 0.0f;
     L.k = 0; L.kd = 0; L.dcount = 1; L.events = 0; L.ctr = 0; L.traj_lo = L.traj_hi = 0; L.out = 0;
-    L.x.w[0] = L.x.w[1] = L.x.w[2] = L.x.w[3] = 0u;
     bool active = false, finished = false;
     // topology as two 25-bit masks + species count in bits 28..31 of `pres`
     // (uniform mode: the warp's topology; mixed mode: this lane's topology)
@@ -676,12 +628,7 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa
         ++n_iters;
 
         // two steps per Philox block (SPEC.md section 3); every lane runs them, parked lanes as no-ops
-#if CT_PHILOX_AHEAD
-        const Philox4 x = L.x;
-        const Philox4 x_next = philox4x32_10_rk(L.ctr, 1u, L.traj_lo, L.traj_hi, A.rk);   // independent of the steps below
-#else
         const Philox4 x = philox4x32_10_rk(L.ctr, 1u, L.traj_lo, L.traj_hi, A.rk);
-#endif
         L.ctr += 1;
         // A warp-wide OR of identical values: the result is warp-uniform by construction, which lets
         // the compiler keep the topology in uniform registers and branch uniformly on its bits.
@@ -697,9 +644,6 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa
         for (int h = 0; h < 2; ++h)
             ssa_step<MM, kAllSpecies, kFast>(L, active, finished, u_pres, u_act, u_nsp, h ? x.w[2] : x.w[0], h ? x.w[3] : x.w[1],
                                       ser, A.nt, A.decim, A.dt);
-#if CT_PHILOX_AHEAD
-        L.x = x_next;
-#endif
     }
     if (A.warp_iters && lane == 0) atomicAdd(A.warp_iters, n_iters);
 }
