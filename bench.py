@@ -153,7 +153,7 @@ def main() -> None:
     ap.add_argument("--mcts-batches", type=int, default=6)
     ap.add_argument("--mcts-depth", type=int, default=3, help="reward batches in flight (virtual loss)")
     ap.add_argument("--mcts-traj", type=int, default=16, help="SSA trajectories per rollout in the MCTS leg")
-    ap.add_argument("--dimer-log2-traj", type=int, default=15, help="trajectories of the dimer-model leg = 2^T (0 = skip)")
+    ap.add_argument("--dimer-log2-traj", type=int, default=20, help="trajectories of the dimer-model leg = 2^T (0 = skip)")
     args = ap.parse_args()
 
     if args.impl == "reference":

@@ -349,33 +349,64 @@ class CircuiTree(ABC):
             if callback is not None and i % callback_every == 0:
                 callback(tree, i, path, sim_node, reward)
 
+    def submit_rewards(self, states: Sequence[Hashable], **kwargs):
+        """Start computing the rewards of a batch of states and return a ticket for
+        :meth:`collect_rewards`.  The default computes them on the spot; subclasses with an
+        asynchronous backend (``OscillationTree``) return at once."""
+        return {"rewards": self.get_rewards(states, **kwargs)}
+
+    def collect_rewards(self, ticket) -> list[float]:
+        return ticket["rewards"]
+
     def search_mcts_batched(self, n_steps: int, batch_size: int, callback: Optional[Callable] = None,
                             callback_every: int = 1, callback_before_start: bool = True,
-                            run_kwargs: Optional[dict] = None) -> None:
+                            run_kwargs: Optional[dict] = None, pipeline_depth: int = 1) -> None:
         """MCTS with ``batch_size`` leaves in flight: each leaf is selected, rolled out and
         visit-back-propagated (virtual loss, the semantics of reference circuitree.py:529-535 under
         ``search_mcts_parallel``), then all rewards come from ONE :meth:`get_rewards` call and are
-        back-propagated in selection order.  ``batch_size=1`` reproduces :meth:`search_mcts`."""
+        back-propagated in selection order.  ``batch_size=1`` reproduces :meth:`search_mcts`.
+
+        ``pipeline_depth > 1`` keeps that many reward batches in flight (:meth:`submit_rewards` /
+        :meth:`collect_rewards`): the next batch is selected, with the visits of every in-flight leaf
+        already counted, while earlier batches are still being simulated."""
         if batch_size < 1:
             raise ValueError("batch_size must be at least 1.")
+        if pipeline_depth < 1:
+            raise ValueError("pipeline_depth must be at least 1.")
         if callback is not None and callback_before_start:
             callback(self, -1, [None], None, None)
         run_kwargs = {} if run_kwargs is None else run_kwargs
-        step = 0
-        while step < n_steps:
-            k = min(batch_size, n_steps - step)
+        inflight: list = []
+        step = 0          # leaves back-propagated
+        selected = 0      # leaves selected
+
+        def retire() -> None:
+            nonlocal step
+            paths, sims, ticket = inflight.pop(0)
+            rewards = self.collect_rewards(ticket)
+            for path, sim, reward in zip(paths, sims, rewards):
+                self.backpropagate_reward(path, reward)
+                if callback is not None and step % callback_every == 0:
+                    callback(self, step, path, sim, reward)
+                step += 1
+
+        while selected < n_steps:
+            k = min(batch_size, n_steps - selected)
             paths, sims = [], []
             for _ in range(k):
                 path = self.select_and_expand()
                 sims.append(self.get_random_terminal_descendant(path[-1]))
                 self.backpropagate_visit(path)
                 paths.append(path)
-            rewards = self.get_rewards(sims, **run_kwargs)
-            for path, sim, reward in zip(paths, sims, rewards):
-                self.backpropagate_reward(path, reward)
-                if callback is not None and step % callback_every == 0:
-                    callback(self, step, path, sim, reward)
-                step += 1
+            selected += k
+            if pipeline_depth == 1:
+                inflight.append((paths, sims, {"rewards": self.get_rewards(sims, **run_kwargs)}))
+            else:
+                inflight.append((paths, sims, self.submit_rewards(sims, **run_kwargs)))
+            while len(inflight) >= pipeline_depth:
+                retire()
+        while inflight:
+            retire()
 
     def search_mcts_parallel(self, n_steps: int, n_threads: int, callback: Optional[Callable] = None,
                              callback_every: int = 1, callback_before_start: bool = True,

@@ -434,10 +434,14 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
         if (per_sm < 1) return fail(CT_ERR_CUDA, "dimer SSA kernel does not fit on an SM (%zu bytes of shared memory)", smem);
         const uint64_t want = (total + ct::kDimThreads - 1) / ct::kDimThreads;
         const uint64_t cap = (uint64_t)eng->n_sm * per_sm;
-        ct::ssa_dimers_kernel<<<(unsigned)(want < cap ? want : cap), ct::kDimThreads, smem, stream>>>(A, d_progs, lay);
+        const unsigned dgrid = (unsigned)(want < cap ? want : cap);
+        uint8_t* d_records = nullptr;      // per-lane record scratch (see ssa_dimers.cuh)
+        CT_CUDA(cudaMallocAsync((void**)&d_records, (size_t)dgrid * ct::kDimThreads * lay.rec_lane_bytes(), stream));
+        ct::ssa_dimers_kernel<<<dgrid, ct::kDimThreads, smem, stream>>>(A, d_progs, lay, d_records);
         CT_CUDA(cudaGetLastError());
         eng->launches += 1;
         // (pageable host memory: the copy above has been staged when cudaMemcpyAsync returns)
+        CT_CUDA(cudaFreeAsync(d_records, stream));
         CT_CUDA(cudaFreeAsync(d_progs, stream));
         CT_CUDA(cudaFreeAsync(d_jobs, stream));
         CT_CUDA(cudaFreeAsync(d_counter, stream));

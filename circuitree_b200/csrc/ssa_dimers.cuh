@@ -7,16 +7,20 @@
 // tiles off a global counter and refill lanes as trajectories end, the finished lane's record is
 // reduced to (reward, lag) by the whole warp.  What differs is where the state lives.  A dimer
 // network has up to 5 TFs, 10 interactions and 10 dimer species whose wiring is data, not code, so
-// the per-lane state vector, the running sum of propensities and the record sit in shared memory
-// as [slot][lane] float arrays (bank = lane: conflict-free for any slot, uniform or per-lane), and
-// the warp walks the job's reaction program with warp-uniform loops:
+// the per-lane state vector and the running sum of propensities sit in shared memory as
+// [slot][lane] float arrays (bank = lane: conflict-free for any slot, uniform or per-lane), and
+// the warp walks the job's reaction program (a few packed words held in registers):
 //   pass 1  running sum in SPEC order: per TF (transcription, mRNA decay, translation, monomer
 //           decay, binding of each interaction at its promoter, unbinding of each), then per dimer
 //           (dimerisation, dissociation); every partial sum is stored;
 //   pass 2  each lane binary-searches its own target in the stored sums (same trip count for all
 //           lanes) and applies the stoichiometry word of the reaction it found: four
-//           (slot, +1/-1) fields, read-modify-write on its own column.
-// Nothing in the hot loop diverges except the rare grid-crossing block.
+//           (slot, +-1 or +-2) fields on distinct slots, loaded together and stored together.
+// Nothing in the hot loop diverges except the rare grid-crossing block.  The kernel is bound by
+// shared-memory latency, so residency matters more than anything else: the per-lane record (the
+// companded block sums, 128 bytes per TF) would take 60 % of a warp's shared memory and is kept in a
+// per-warp scratch area in global memory instead (one byte per TF every 16 grid points: ~500 bytes
+// per ~5e5 events, L2-resident); that raises residency from 8 to ~20 warps per SM.
 #pragma once
 #include <string.h>
 
@@ -36,98 +40,123 @@ struct DimerTopo {                  // 56 bytes
     uint8_t pad[2];
 };
 
-// state slots of one lane (floats holding exact small integers)
-enum : int { kSlotP = 0, kSlotR = 5, kSlotD = 10, kSlotB = 20, kSlotN = 30, kSlotA = 35, kSlotBlk = 40, kSlotDummy = 45, kSlots = 46 };
+// state slots of one lane (floats holding exact small integers); four dummies so that the four
+// fields of a stoichiometry word never share a slot
+enum : int { kSlotP = 0, kSlotR = 5, kSlotD = 10, kSlotB = 20, kSlotN = 30, kSlotA = 35, kSlotBlk = 40, kSlotDummy = 45, kSlots = 49 };
 
 // The job's reaction program, built on the host from a DimerTopo (dimer_program below).
-struct DimerProg {                  // one per job
+struct DimerProg {                  // 272 bytes, one per job
+    uint64_t pk_ix_dim;             // dimer of sorted interaction x at bits 4x (interactions sorted by target, stable)
+    uint32_t pk_ix_start;           // TF s owns sorted interactions [start(s), start(s+1)), start(s) at bits 4s (s = 0..5)
+    uint32_t pk_dim_a, pk_dim_b;    // monomers of dimer d at bits 3d
     uint8_t n_tf, n_ixn, n_dim, n_entries;
-    uint8_t ix_start[kMaxSpecies + 1];   // interactions sorted by target (stable): TF s owns x in [ix_start[s], ix_start[s+1])
-    uint8_t search_iters;                // ceil(log2(n_entries + 1))
-    uint8_t pad0;
-    uint8_t ix_dim[kMaxIxn];             // dimer of sorted interaction x
-    uint8_t pad1[2];
-    uint8_t dim_a[kMaxIxn], dim_b[kMaxIxn];
-    uint32_t stoich[kMaxEntries + 1];    // reaction -> 4 x (slot | code << 6), code 1 = +1, 2 = -1; entry n_entries = none
+    uint8_t search_iters;           // ceil(log2(n_entries + 1))
+    uint8_t pad[3];
+    // reaction -> 4 x (slot | code << 6) on distinct slots; code 0 = +1, 1 = -1, 2 = +2, 3 = -2
+    // (a dummy slot absorbs unused fields); entry n_entries = "no reaction"
+    uint32_t stoich[kMaxEntries + 1];
 };
-static_assert(sizeof(DimerProg) % 4 == 0, "DimerProg is copied word by word");
+static_assert(sizeof(DimerProg) % 8 == 0, "DimerProg is copied word by word and holds a 64-bit member");
 
 inline DimerProg dimer_program(const DimerTopo& T)
 {
     DimerProg G;
     memset(&G, 0, sizeof G);
     G.n_tf = T.n_tf; G.n_ixn = T.n_ixn; G.n_dim = T.n_dim;
-    int sorted[kMaxIxn], nx = 0;
+    int sorted[kMaxIxn], start[kMaxSpecies + 1], nx = 0;
     for (int s = 0; s < T.n_tf; ++s) {
-        G.ix_start[s] = (uint8_t)nx;
+        start[s] = nx;
         for (int e = 0; e < T.n_ixn; ++e)
             if (T.ix_tgt[e] == s) sorted[nx++] = e;
     }
-    for (int s = T.n_tf; s <= kMaxSpecies; ++s) G.ix_start[s] = (uint8_t)nx;
-    for (int x = 0; x < nx; ++x) G.ix_dim[x] = T.ix_dim[sorted[x]];
-    for (int d = 0; d < T.n_dim; ++d) { G.dim_a[d] = T.dim_a[d]; G.dim_b[d] = T.dim_b[d]; }
-    const uint32_t none = (uint32_t)kSlotDummy;
-    auto word = [&](uint32_t f0, uint32_t f1 = kSlotDummy, uint32_t f2 = kSlotDummy, uint32_t f3 = kSlotDummy) {
+    for (int s = T.n_tf; s <= kMaxSpecies; ++s) start[s] = nx;
+    for (int s = 0; s <= kMaxSpecies; ++s) G.pk_ix_start |= (uint32_t)start[s] << (4 * s);
+    for (int x = 0; x < nx; ++x) G.pk_ix_dim |= (uint64_t)T.ix_dim[sorted[x]] << (4 * x);
+    for (int d = 0; d < T.n_dim; ++d) {
+        G.pk_dim_a |= (uint32_t)T.dim_a[d] << (3 * d);
+        G.pk_dim_b |= (uint32_t)T.dim_b[d] << (3 * d);
+    }
+    auto word = [&](uint32_t f0, uint32_t f1 = kSlotDummy + 1, uint32_t f2 = kSlotDummy + 2, uint32_t f3 = kSlotDummy + 3) {
         return f0 | (f1 << 8) | (f2 << 16) | (f3 << 24);
     };
-    auto inc = [](int slot) { return (uint32_t)slot | (1u << 6); };
-    auto dec = [](int slot) { return (uint32_t)slot | (2u << 6); };
+    auto inc = [](int slot) { return (uint32_t)slot; };
+    auto dec = [](int slot) { return (uint32_t)slot | (1u << 6); };
+    auto inc2 = [](int slot) { return (uint32_t)slot | (2u << 6); };
+    auto dec2 = [](int slot) { return (uint32_t)slot | (3u << 6); };
     int r = 0;
     for (int s = 0; s < T.n_tf; ++s) {
         G.stoich[r++] = word(inc(kSlotR + s));
         G.stoich[r++] = word(dec(kSlotR + s));
         G.stoich[r++] = word(inc(kSlotP + s));
         G.stoich[r++] = word(dec(kSlotP + s));
-        for (int x = G.ix_start[s]; x < G.ix_start[s + 1]; ++x) {
-            const bool act = T.ix_act[sorted[x]] != 0;
-            G.stoich[r++] = word(dec(kSlotD + G.ix_dim[x]), inc(kSlotB + x), inc(kSlotN + s), act ? inc(kSlotA + s) : none);
+        for (int x = start[s]; x < start[s + 1]; ++x) {
+            const int e = sorted[x];
+            G.stoich[r++] = word(dec(kSlotD + T.ix_dim[e]), inc(kSlotB + x), inc(kSlotN + s),
+                                 T.ix_act[e] ? inc(kSlotA + s) : (uint32_t)(kSlotDummy + 3));
         }
-        for (int x = G.ix_start[s]; x < G.ix_start[s + 1]; ++x) {
-            const bool act = T.ix_act[sorted[x]] != 0;
-            G.stoich[r++] = word(inc(kSlotD + G.ix_dim[x]), dec(kSlotB + x), dec(kSlotN + s), act ? dec(kSlotA + s) : none);
+        for (int x = start[s]; x < start[s + 1]; ++x) {
+            const int e = sorted[x];
+            G.stoich[r++] = word(inc(kSlotD + T.ix_dim[e]), dec(kSlotB + x), dec(kSlotN + s),
+                                 T.ix_act[e] ? dec(kSlotA + s) : (uint32_t)(kSlotDummy + 3));
         }
     }
     for (int d = 0; d < T.n_dim; ++d) {
-        G.stoich[r++] = word(dec(kSlotP + T.dim_a[d]), dec(kSlotP + T.dim_b[d]), inc(kSlotD + d));
-        G.stoich[r++] = word(inc(kSlotP + T.dim_a[d]), inc(kSlotP + T.dim_b[d]), dec(kSlotD + d));
+        const int a = T.dim_a[d], b = T.dim_b[d];
+        if (a != b) {
+            G.stoich[r++] = word(dec(kSlotP + a), dec(kSlotP + b), inc(kSlotD + d));
+            G.stoich[r++] = word(inc(kSlotP + a), inc(kSlotP + b), dec(kSlotD + d));
+        } else {
+            G.stoich[r++] = word(dec2(kSlotP + a), (uint32_t)(kSlotDummy + 1), inc(kSlotD + d));
+            G.stoich[r++] = word(inc2(kSlotP + a), (uint32_t)(kSlotDummy + 1), dec(kSlotD + d));
+        }
     }
     G.n_entries = (uint8_t)r;
-    G.stoich[r] = word(none);
+    G.stoich[r] = word((uint32_t)kSlotDummy);
     int it = 0;
     while ((1 << it) < r + 1) ++it;
     G.search_iters = (uint8_t)it;
     return G;
 }
 
-// shared memory of one warp, sized per launch: record | state | running sums | reward scratch | program
+// Per-launch sizes.  Shared memory of one warp: state | running sums | reward scratch | program;
+// the records live in global scratch, ser_species * 128 bytes per resident lane.
 struct DimerLayout {
     int32_t ser_species;      // species rows in the per-lane record (max n_tf of the launch)
     int32_t cum_slots;        // max n_entries of the launch + 1 (the +inf sentinel)
-    __host__ __device__ size_t ser_bytes() const { return (size_t)32 * ser_species * kSerStride; }
+    __host__ __device__ size_t rec_lane_bytes() const { return (size_t)ser_species * kSerStride; }
     __host__ __device__ size_t warp_bytes() const
     {
-        return ser_bytes() + (size_t)(kSlots + cum_slots) * 32 * sizeof(float) + kSerStride * sizeof(float) + sizeof(DimerProg);
+        return (size_t)(kSlots + cum_slots) * 32 * sizeof(float) + kSerStride * sizeof(float) + sizeof(DimerProg) +
+               (size_t)kMaxSpecies * kSerStride;      // ... | staging copy of one finished record
     }
 };
 
-__global__ void __launch_bounds__(kDimThreads) ssa_dimers_kernel(const LaunchArgs A, const DimerProg* __restrict__ progs,
-                                                                 const DimerLayout lay)
+// delta of a stoichiometry field: code 0 = +1, 1 = -1, 2 = +2, 3 = -2 (built from the float's bits)
+__device__ __forceinline__ float stoich_delta(uint32_t code)
+{
+    return __uint_as_float((0x3f800000u + ((code & 2u) << 22)) | (code << 31));
+}
+
+__global__ void __launch_bounds__(kDimThreads, 10) ssa_dimers_kernel(const LaunchArgs A, const DimerProg* __restrict__ progs,
+                                                                 const DimerLayout lay, uint8_t* __restrict__ records)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     uint8_t* wbase = smem + (size_t)warp * lay.warp_bytes();
-    uint8_t* warp_ser = wbase;
-    const int ser_lane_bytes = lay.ser_species * kSerStride;
-    uint8_t* ser = warp_ser + (size_t)lane * ser_lane_bytes;
-    float* X = reinterpret_cast<float*>(wbase + lay.ser_bytes()) + lane;     // slot s of this lane: X[s * 32]
-    float* cum = X + kSlots * 32;                                            // partial sum r of this lane: cum[r * 32]
-    float* z = reinterpret_cast<float*>(wbase + lay.ser_bytes()) + (kSlots + lay.cum_slots) * 32;
+    float* X = reinterpret_cast<float*>(wbase) + lane;        // slot s of this lane: X[s * 32]
+    float* cum = X + kSlots * 32;                             // partial sum r of this lane: cum[r * 32]
+    float* z = reinterpret_cast<float*>(wbase) + (kSlots + lay.cum_slots) * 32;
     DimerProg* G = reinterpret_cast<DimerProg*>(z + kSerStride);
+    uint8_t* stage = reinterpret_cast<uint8_t*>(G) + sizeof(DimerProg);
+    // records of this warp's 32 lanes (global scratch, see the header comment)
+    const size_t ser_lane_bytes = lay.rec_lane_bytes();
+    uint8_t* warp_ser = records + ((size_t)blockIdx.x * (kDimThreads / 32) + warp) * 32 * ser_lane_bytes;
+    uint8_t* ser = warp_ser + (size_t)lane * ser_lane_bytes;
 
     // per-lane rate constants (zero = parked lane: nothing fires)
-    float k_on = 0.f, k_off1 = 0.f, k_off2 = 0.f, km0 = 0.f, km1 = 0.f, km2 = 0.f, km3 = 0.f, kp = 0.f, gm = 0.f, gp = 0.f,
-          k_dim = 0.f, k_undim = 0.f;
+    float k_on = 0.f, k_on2 = 0.f, k_off1 = 0.f, k_off2 = 0.f, km0 = 0.f, km1 = 0.f, km2 = 0.f, km3 = 0.f, kp = 0.f, gm = 0.f,
+          gp = 0.f, k_dim = 0.f, k_undim = 0.f;
     float t_rem = 0.0f;
     int k = 0, kd = 0, dcount = 1;
     uint32_t events = 0, ctr = 0, traj_lo = 0, traj_hi = 0, out = 0;
@@ -141,7 +170,10 @@ __global__ void __launch_bounds__(kDimThreads) ssa_dimers_kernel(const LaunchArg
     Job pend = job;
     uint32_t pos = 0, end = 0, pend_pos = 0, pend_end = 0, pend_job = 0;
     bool have_pending = false, out_of_work = false;
+    // the current job's program, in registers (warp-uniform values)
     int n_tf = 0, n_dim = 0, n_entries = 0, search_iters = 0;
+    uint32_t pk_ix_start = 0, pk_dim_a = 0, pk_dim_b = 0;
+    uint64_t pk_ix_dim = 0;
     uint32_t n_iters = 0;
 
     for (;;) {
@@ -149,18 +181,23 @@ __global__ void __launch_bounds__(kDimThreads) ssa_dimers_kernel(const LaunchArg
         if (idle) {
             // 1. reduce finished trajectories to (reward, lag), one lane at a time, whole warp helping
             unsigned fin = __ballot_sync(kFull, finished);
+            if (fin) __syncwarp();     // the finished lanes' record bytes are visible to the whole warp
             while (fin) {
                 const int src = __ffs(fin) - 1;
                 fin &= fin - 1;
                 float rw; int lg;
-                const uint8_t* sser = warp_ser + (size_t)src * ser_lane_bytes;
-                warp_reward(sser, z, n_tf, A.n_dec, lane, rw, lg);
+                // stage the record in shared memory (L2 reads: another lane wrote it), then reduce it
+                const uint32_t* grec = reinterpret_cast<const uint32_t*>(warp_ser + (size_t)src * ser_lane_bytes);
+                for (int w = lane; w < n_tf * (kSerStride / 4); w += 32) reinterpret_cast<uint32_t*>(stage)[w] = __ldcg(grec + w);
+                __syncwarp();
+                warp_reward(stage, z, n_tf, A.n_dec, lane, rw, lg);
                 const uint32_t o = __shfl_sync(kFull, out, src);
                 if (A.series) {
                     for (int s = 0; s < n_tf; ++s)
                         for (int q = lane; q < A.n_dec; q += 32)
-                            A.series[(size_t)o * A.series_stride + s * A.n_dec + q] = sser[s * kSerStride + q];
+                            A.series[(size_t)o * A.series_stride + s * A.n_dec + q] = stage[s * kSerStride + q];
                 }
+                __syncwarp();
                 if (lane == src) {
                     A.reward[o] = rw;
                     if (A.lag) A.lag[o] = lg;
@@ -183,7 +220,8 @@ __global__ void __launch_bounds__(kDimThreads) ssa_dimers_kernel(const LaunchArg
                         out = slot;
                         float prm[12];
                         trajectory_params(A, traj_lo, traj_hi, slot, prm);
-                        k_on = prm[0]; k_off1 = prm[1]; k_off2 = prm[2]; km0 = prm[3]; km1 = prm[4]; km2 = prm[5]; km3 = prm[6];
+                        k_on = prm[0]; k_on2 = 2.0f * prm[0]; k_off1 = prm[1]; k_off2 = prm[2];
+                        km0 = prm[3]; km1 = prm[4]; km2 = prm[5]; km3 = prm[6];
                         kp = prm[7]; gm = prm[8]; gp = prm[9]; k_dim = prm[10]; k_undim = prm[11];
 #pragma unroll 1
                         for (int s = 0; s < kSlots; ++s) X[s * 32] = 0.0f;
@@ -237,13 +275,14 @@ __global__ void __launch_bounds__(kDimThreads) ssa_dimers_kernel(const LaunchArg
                     const bool drained = (__ballot_sync(kFull, active) == 0u);
                     if (same || drained) {
                         if (!same) {
-                            // switch topology: copy the job's program into the warp's shared memory
+                            // switch topology: the stoichiometry table goes to shared memory, the rest to registers
                             const uint32_t* src = reinterpret_cast<const uint32_t*>(progs + pend_job);
                             uint32_t* dst = reinterpret_cast<uint32_t*>(G);
                             __syncwarp();
                             for (int w = lane; w < (int)(sizeof(DimerProg) / 4); w += 32) dst[w] = src[w];
                             __syncwarp();
                             n_tf = G->n_tf; n_dim = G->n_dim; n_entries = G->n_entries; search_iters = G->search_iters;
+                            pk_ix_start = G->pk_ix_start; pk_dim_a = G->pk_dim_a; pk_dim_b = G->pk_dim_b; pk_ix_dim = G->pk_ix_dim;
                             cum[n_entries * 32] = 3.4e38f;    // sentinel (every lane): "no reaction" is always found
                         }
                         job = pend; pos = pend_pos; end = pend_end;
@@ -265,30 +304,35 @@ __global__ void __launch_bounds__(kDimThreads) ssa_dimers_kernel(const LaunchArg
             // ---- pass 1: running sum of propensities in SPEC order, every partial sum stored ----
             float c = 0.0f;
             float* cp = cum;
+#pragma unroll
+            for (int s = 0; s < kMaxSpecies; ++s) {
+                if (s < n_tf) {      // warp-uniform
+                    const float n = X[(kSlotN + s) * 32], na = X[(kSlotA + s) * 32];
+                    const float r = X[(kSlotR + s) * 32], p = X[(kSlotP + s) * 32];
+                    const float km_a = (na > 0.0f) ? km1 : km0;
+                    const float km_i = (na > 0.0f) ? km3 : km2;
+                    c += (n > na) ? km_i : km_a;    cp[0] = c;
+                    c = fmaf(gm, r, c);             cp[32] = c;
+                    c = fmaf(kp, r, c);             cp[64] = c;
+                    c = fmaf(gp, p, c);             cp[96] = c;
+                    cp += 128;
+                    const int x0 = (pk_ix_start >> (4 * s)) & 15, x1 = (pk_ix_start >> (4 * s + 4)) & 15;
+                    if (x1 > x0) {
+                        const float kfree = fmaf(-k_on, n, k_on2);            // k_on (2 - n)
+                        const float koff = (n >= 2.0f) ? k_off2 : k_off1;
 #pragma unroll 1
-            for (int s = 0; s < n_tf; ++s) {
-                const float n = X[(kSlotN + s) * 32], na = X[(kSlotA + s) * 32];
-                const float r = X[(kSlotR + s) * 32], p = X[(kSlotP + s) * 32];
-                const float km_a = (na > 0.0f) ? km1 : km0;
-                const float km_i = (na > 0.0f) ? km3 : km2;
-                c += (n > na) ? km_i : km_a;    cp[0] = c;
-                c = fmaf(gm, r, c);             cp[32] = c;
-                c = fmaf(kp, r, c);             cp[64] = c;
-                c = fmaf(gp, p, c);             cp[96] = c;
-                cp += 128;
-                const int x0 = G->ix_start[s], x1 = G->ix_start[s + 1];
-                if (x1 > x0) {
-                    const float kfree = k_on * (2.0f - n);
-                    const float koff = (n >= 2.0f) ? k_off2 : k_off1;
+                        for (int q = x0; q < x1; ++q) {
+                            const int d = (int)(pk_ix_dim >> (4 * q)) & 15;
+                            c = fmaf(kfree, X[(kSlotD + d) * 32], c); *cp = c; cp += 32;
+                        }
 #pragma unroll 1
-                    for (int q = x0; q < x1; ++q) { c = fmaf(kfree, X[(kSlotD + G->ix_dim[q]) * 32], c); *cp = c; cp += 32; }
-#pragma unroll 1
-                    for (int q = x0; q < x1; ++q) { c = fmaf(koff, X[(kSlotB + q) * 32], c); *cp = c; cp += 32; }
+                        for (int q = x0; q < x1; ++q) { c = fmaf(koff, X[(kSlotB + q) * 32], c); *cp = c; cp += 32; }
+                    }
                 }
             }
 #pragma unroll 1
             for (int d = 0; d < n_dim; ++d) {
-                const int da = G->dim_a[d], db = G->dim_b[d];
+                const int da = (pk_dim_a >> (3 * d)) & 7, db = (pk_dim_b >> (3 * d)) & 7;
                 const float pa = X[(kSlotP + da) * 32], pb = X[(kSlotP + db) * 32];
                 const float pairs = (da != db) ? pa * pb : 0.5f * pa * (pa - 1.0f);
                 c = fmaf(k_dim, pairs, c);                      cp[0] = c;
@@ -304,8 +348,9 @@ __global__ void __launch_bounds__(kDimThreads) ssa_dimers_kernel(const LaunchArg
             const bool was_active = active;
             if (active && t_rem < 0.0f) {
                 do {
-#pragma unroll 1
-                    for (int s = 0; s < n_tf; ++s) X[(kSlotBlk + s) * 32] += fminf(X[(kSlotP + s) * 32], kSampleCap);
+#pragma unroll
+                    for (int s = 0; s < kMaxSpecies; ++s)
+                        if (s < n_tf) X[(kSlotBlk + s) * 32] += fminf(X[(kSlotP + s) * 32], kSampleCap);
                     k += 1;
                     if (--dcount == 0) {
                         dcount = A.decim;
@@ -331,17 +376,20 @@ __global__ void __launch_bounds__(kDimThreads) ssa_dimers_kernel(const LaunchArg
                 hi = lt ? mid : hi;
                 lo = lt ? lo : mid + 1;
             }
-            uint32_t sw = G->stoich[lo];
-#pragma unroll
-            for (int f = 0; f < 4; ++f) {
-                const uint32_t slot = sw & 63u, code = (sw >> 6) & 3u;
-                const float delta = (float)(int)(code & 1u) - (float)(int)(code >> 1);
-                X[slot * 32] += delta;
-                sw >>= 8;
-            }
+            const uint32_t sw = G->stoich[lo];
+            // the four fields name distinct slots: load all, then store all
+            float* f0 = X + (sw & 63u) * 32;
+            float* f1 = X + ((sw >> 8) & 63u) * 32;
+            float* f2 = X + ((sw >> 16) & 63u) * 32;
+            float* f3 = X + ((sw >> 24) & 63u) * 32;
+            const float v0 = *f0, v1 = *f1, v2 = *f2, v3 = *f3;
+            *f0 = v0 + stoich_delta((sw >> 6) & 3u);
+            *f1 = v1 + stoich_delta((sw >> 14) & 3u);
+            *f2 = v2 + stoich_delta((sw >> 22) & 3u);
+            *f3 = v3 + stoich_delta((sw >> 30) & 3u);
             events += (was_active && alive) ? 1u : 0u;
             if (!alive) {   // park: zero rates and state so that the lane idles through the lock-step loop
-                k_on = k_off1 = k_off2 = km0 = km1 = km2 = km3 = kp = gm = gp = k_dim = k_undim = 0.0f;
+                k_on = k_on2 = k_off1 = k_off2 = km0 = km1 = km2 = km3 = kp = gm = gp = k_dim = k_undim = 0.0f;
 #pragma unroll 1
                 for (int s = 0; s < kSlots; ++s) X[s * 32] = 0.0f;
                 t_rem = 0.0f;

@@ -224,43 +224,14 @@ class NativeTree:
         """Start the reward batch of a set of selected leaves (asynchronous on the GPU path)."""
         if self.reward_fn is not None:
             return {"rewards": np.asarray(self.reward_fn([self.key_to_string(int(k)) for k in keys]), dtype=np.float64)}
-        eng = self.reward_engine
-        # group leaves by topology: one job per distinct simulated state ...
-        uniq, inverse, counts = np.unique(handles, return_inverse=True, return_counts=True)
-        # ... with the events per trajectory seen so far for that topology as the cost hint of the
-        # longest-first launch order (unseen topologies: assume expensive)
-        cost = np.array([eng.cost.get(int(h), np.inf) for h in uniq])
-        known = cost[np.isfinite(cost)]
-        job_cost = np.where(np.isfinite(cost), cost, float(known.max()) if len(known) else 1.0e6)
-        B = self.trajectories_per_reward
-        n_traj = (counts * B).astype(np.uint32)
-        offsets = np.concatenate(([0], np.cumsum(n_traj, dtype=np.uint64)[:-1])).astype(np.uint64)
-        bases = offsets + np.uint64(eng.next_traj)
-        eng.next_traj += int(n_traj.sum())
-        ticket = eng.engine.submit(uniq, n_traj, bases, eng.cfg, eng.seed, job_cost=job_cost)
-        return {"ticket": ticket, "uniq": uniq, "inverse": inverse, "n_traj": n_traj, "offsets": offsets, "n_leaves": len(keys)}
+        return self.reward_engine.submit_leaves(handles, self.trajectories_per_reward)
 
     def _collect(self, job: dict) -> np.ndarray:
         """Wait for a reward batch; leaf x of topology u gets the mean of its own block of
         ``trajectories_per_reward`` trajectories."""
         if "rewards" in job:
             return job["rewards"]
-        eng = self.reward_engine
-        out = eng.engine.wait(job["ticket"], per_trajectory=True)
-        eng.total_events += int(out["job_events"].sum())
-        eng.total_trajectories += int(job["n_traj"].sum())
-        for h, ev, nt in zip(job["uniq"], out["job_events"], job["n_traj"]):
-            eng.cost[int(h)] = float(ev) / float(nt)
-        B = self.trajectories_per_reward
-        block_means = out["reward"].astype(np.float64).reshape(-1, B).mean(axis=1)
-        first_block = (job["offsets"] // np.uint64(B)).astype(np.int64)
-        inverse = job["inverse"]
-        # rank of each leaf among the leaves that share its topology, in selection order
-        order = np.argsort(inverse, kind="stable")
-        rank = np.empty(len(inverse), dtype=np.int64)
-        starts = np.concatenate(([0], np.cumsum(np.bincount(inverse, minlength=len(job["uniq"])))[:-1]))
-        rank[order] = np.arange(len(inverse)) - starts[inverse[order]]
-        return block_means[first_block[inverse] + rank]
+        return self.reward_engine.collect_leaves(job)
 
     def _rewards(self, keys: np.ndarray, handles: np.ndarray) -> np.ndarray:
         return self._collect(self._submit(keys, handles))

@@ -81,6 +81,46 @@ class RewardEngine:
         return out
 
 
+    # -- asynchronous batches of leaves (pipelined MCTS) ---------------------------------------------------
+    def submit_leaves(self, handles: np.ndarray, trajectories_per_leaf: int) -> dict:
+        """Start the reward batch of a set of selected leaves (one topology handle per leaf) and
+        return at once.  Leaves are grouped by topology: one job per distinct simulated state, with
+        the events per trajectory seen so far for that topology as the cost hint of the
+        longest-first launch order (unseen topologies: assume expensive)."""
+        handles = np.asarray(handles, dtype=np.uint64)
+        uniq, inverse, counts = np.unique(handles, return_inverse=True, return_counts=True)
+        cost = np.array([self.cost.get(int(h), np.inf) for h in uniq])
+        known = cost[np.isfinite(cost)]
+        job_cost = np.where(np.isfinite(cost), cost, float(known.max()) if len(known) else 1.0e6)
+        B = int(trajectories_per_leaf)
+        n_traj = (counts * B).astype(np.uint32)
+        offsets = np.concatenate(([0], np.cumsum(n_traj, dtype=np.uint64)[:-1])).astype(np.uint64)
+        bases = offsets + np.uint64(self.next_traj)
+        self.next_traj += int(n_traj.sum())
+        ticket = self.engine.submit(uniq, n_traj, bases, self.cfg, self.seed, job_cost=job_cost)
+        return {"ticket": ticket, "uniq": uniq, "inverse": inverse, "n_traj": n_traj, "offsets": offsets,
+                "n_leaves": len(handles), "B": B}
+
+    def collect_leaves(self, job: dict) -> np.ndarray:
+        """Wait for a batch started by :meth:`submit_leaves`; leaf x of topology u gets the mean of
+        its own block of ``trajectories_per_leaf`` trajectories (float64, in leaf order)."""
+        out = self.engine.wait(job["ticket"], per_trajectory=True)
+        self.total_events += int(out["job_events"].sum())
+        self.total_trajectories += int(job["n_traj"].sum())
+        for h, ev, nt in zip(job["uniq"], out["job_events"], job["n_traj"]):
+            self.cost[int(h)] = float(ev) / float(nt)
+        B = job["B"]
+        block_means = out["reward"].astype(np.float64).reshape(-1, B).mean(axis=1)
+        first_block = (job["offsets"] // np.uint64(B)).astype(np.int64)
+        inverse = job["inverse"]
+        # rank of each leaf among the leaves that share its topology, in selection order
+        order = np.argsort(inverse, kind="stable")
+        rank = np.empty(len(inverse), dtype=np.int64)
+        starts = np.concatenate(([0], np.cumsum(np.bincount(inverse, minlength=len(job["uniq"])))[:-1]))
+        rank[order] = np.arange(len(inverse)) - starts[inverse[order]]
+        return block_means[first_block[inverse] + rank]
+
+
 class OscillationTree(CircuiTree):
     """MCTS for oscillating TF networks with the reward computed on the GPU.
 
@@ -111,6 +151,15 @@ class OscillationTree(CircuiTree):
     def get_rewards(self, states: Sequence[Hashable], **kwargs) -> list[float]:
         out = self._reward_engine.run(list(states), self.trajectories_per_reward)
         return [float(x) for x in out["job_mean"]]
+
+    def submit_rewards(self, states: Sequence[Hashable], **kwargs):
+        """Asynchronous half of :meth:`get_rewards` (used by ``search_mcts_batched(pipeline_depth > 1)``):
+        the batch starts on a stream of its own and this returns at once."""
+        handles = np.array([self._reward_engine.handle(s) for s in states], dtype=np.uint64)
+        return self._reward_engine.submit_leaves(handles, self.trajectories_per_reward)
+
+    def collect_rewards(self, ticket) -> list[float]:
+        return [float(x) for x in self._reward_engine.collect_leaves(ticket)]
 
     def simulate(self, states: Sequence[Hashable], n_traj: int, params: Optional[np.ndarray] = None) -> dict:
         """Per-trajectory rewards and lags for analysis (not part of the reference API)."""

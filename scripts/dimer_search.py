@@ -1,0 +1,48 @@
+"""BASELINE config 3: DimersGrammar oscillation search on one B200.
+
+    python scripts/dimer_search.py [--rollouts 100000] [--batch 8192] [--traj 8] [--depth 3]
+
+Five transcription factors (three components A, B, C and two regulators D, E), activating and
+inhibiting dimer interactions, at most two per promoter (the DimersGrammar default).  The tree is
+the Python mirror of the reference (its DimersGrammar state strings and actions); every batch of
+leaves is one launch of the dimer-model kernel (SPEC.md section 9), several batches in flight.
+Prints one JSON line: rollouts/s, SSA reaction-steps/s, and the best terminal states found.
+"""
+import argparse, json, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+from circuitree_b200 import DimersGrammar, OscillationTree
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--rollouts", type=int, default=100_000)
+ap.add_argument("--batch", type=int, default=8192)
+ap.add_argument("--traj", type=int, default=8, help="SSA trajectories per rollout")
+ap.add_argument("--depth", type=int, default=3, help="reward batches in flight")
+ap.add_argument("--components", default="ABC")
+ap.add_argument("--regulators", default="DE")
+ap.add_argument("--seed", type=int, default=0)
+args = ap.parse_args()
+
+grammar = DimersGrammar(components=list(args.components), regulators=list(args.regulators),
+                        interactions=["activates", "inhibits"])
+root = f"{args.components}+{args.regulators}::"
+tree = OscillationTree(grammar=grammar, root=root, seed=args.seed, n_exhausted=np.inf, trajectories_per_reward=args.traj)
+tree.search_mcts_batched(min(256, args.rollouts), 256)                      # warm-up (engine, handles)
+eng = tree.reward_engine
+ev0, tr0, v0 = eng.total_events, eng.total_trajectories, tree.graph.nodes[root]["visits"]
+t0 = time.perf_counter()
+tree.search_mcts_batched(args.rollouts, args.batch, pipeline_depth=args.depth)
+dt = time.perf_counter() - t0
+terminals = [(n, d["reward"] / d["visits"], d["visits"]) for n, d in tree.graph.nodes(data=True)
+             if isinstance(n, str) and n.startswith("*") and d["visits"] >= 20]
+terminals.sort(key=lambda x: -x[1])
+print(json.dumps({
+    "config": f"DimersGrammar {root} activates/inhibits, {args.rollouts} rollouts, batch {args.batch}, "
+              f"{args.traj} trajectories per rollout, {args.depth} batches in flight",
+    "seconds": round(dt, 2), "rollouts_per_s": args.rollouts / dt,
+    "reaction_steps_per_s": (eng.total_events - ev0) / dt, "trajectories": eng.total_trajectories - tr0,
+    "events_per_trajectory": (eng.total_events - ev0) / max(1, eng.total_trajectories - tr0),
+    "tree_nodes": tree.graph.number_of_nodes(), "root_visits": tree.graph.nodes[root]["visits"] - v0,
+    "distinct_topologies_simulated": len(eng._handles),
+    "best": [[n, round(r, 4), v] for n, r, v in terminals[:5]],
+}))

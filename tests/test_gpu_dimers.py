@@ -215,3 +215,18 @@ def test_get_reward_through_circuitree_api_with_dimers_grammar():
     tree.search_mcts_batched(64, 32)
     assert tree.graph.nodes["ABC+R::"]["visits"] == 64
     assert 0.0 < tree.graph.nodes["ABC+R::"]["reward"] / 64 < 1.0
+
+
+def test_pipelined_search_with_dimers_grammar():
+    """search_mcts_batched(pipeline_depth=3): asynchronous dimer-kernel batches behind the Python tree."""
+    def run():
+        c = small_cfg(nt=480, decim=16)
+        t = OscillationTree(grammar=GRAMMAR, root="ABC+R::", seed=4, n_exhausted=np.inf, trajectories_per_reward=8, sim_config=c)
+        t.search_mcts_batched(192, 32, pipeline_depth=3)
+        return t
+    a, b = run(), run()
+    assert a.graph.nodes["ABC+R::"]["visits"] == 192
+    assert a.reward_engine.total_trajectories == 192 * 8
+    assert 0.0 < a.graph.nodes["ABC+R::"]["reward"] / 192 < 1.0
+    assert sorted((n, d["visits"], d["reward"]) for n, d in a.graph.nodes(data=True)) == \
+        sorted((n, d["visits"], d["reward"]) for n, d in b.graph.nodes(data=True))

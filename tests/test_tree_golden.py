@@ -211,3 +211,44 @@ def test_missing_root_in_supplied_graph():
 
     with pytest.raises(ValueError):
         CrcTree(grammar=grammar(2), root="AB::", graph=nx.DiGraph())
+
+
+def test_pipelined_batched_search_keeps_virtual_loss_bookkeeping():
+    """search_mcts_batched(pipeline_depth > 1): several reward batches in flight (submit_rewards /
+    collect_rewards); every selected leaf is visited once and rewarded once, deterministically."""
+    from circuitree_b200 import CircuiTree, SimpleNetworkGrammar
+
+    class Stub(CircuiTree):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            self.submitted, self.collected, self.handed_out = 0, 0, 0.0
+
+        def get_reward(self, state, **kw):
+            r = (sum(map(ord, state)) % 7) / 7.0
+            self.handed_out += r
+            return r
+
+        def submit_rewards(self, states, **kw):
+            self.submitted += 1
+            assert self.submitted - self.collected <= 3          # at most pipeline_depth batches in flight
+            return super().submit_rewards(states, **kw)
+
+        def collect_rewards(self, ticket):
+            self.collected += 1
+            return super().collect_rewards(ticket)
+
+    def run(depth):
+        g = SimpleNetworkGrammar(list("ABC"), ["activates", "inhibits"], root="ABC::")
+        t = Stub(grammar=g, root="ABC::", seed=3, n_exhausted=np.inf)
+        t.search_mcts_batched(500, 32, pipeline_depth=depth)
+        return t
+
+    a, b, c = run(3), run(3), run(1)
+    assert a.submitted == a.collected == 16 and c.submitted == 0
+    for t in (a, c):
+        assert t.graph.nodes["ABC::"]["visits"] == 500
+        assert abs(t.handed_out - t.graph.nodes["ABC::"]["reward"]) < 1e-9      # every reward reached the root once
+    assert sorted((n, d["visits"], d["reward"]) for n, d in a.graph.nodes(data=True)) == \
+        sorted((n, d["visits"], d["reward"]) for n, d in b.graph.nodes(data=True))
+    with pytest.raises(ValueError):
+        c.search_mcts_batched(10, 4, pipeline_depth=0)
