@@ -383,7 +383,7 @@ class CircuiTree(ABC):
         def retire() -> None:
             nonlocal step
             paths, sims, ticket = inflight.pop(0)
-            rewards = self.collect_rewards(ticket)
+            rewards = ticket if isinstance(ticket, list) else self.collect_rewards(ticket)
             for path, sim, reward in zip(paths, sims, rewards):
                 self.backpropagate_reward(path, reward)
                 if callback is not None and step % callback_every == 0:
@@ -400,7 +400,7 @@ class CircuiTree(ABC):
                 paths.append(path)
             selected += k
             if pipeline_depth == 1:
-                inflight.append((paths, sims, {"rewards": self.get_rewards(sims, **run_kwargs)}))
+                inflight.append((paths, sims, list(self.get_rewards(sims, **run_kwargs))))
             else:
                 inflight.append((paths, sims, self.submit_rewards(sims, **run_kwargs)))
             while len(inflight) >= pipeline_depth:

@@ -16,7 +16,7 @@ from circuitree_b200 import DimersGrammar, OscillationTree
 ap = argparse.ArgumentParser()
 ap.add_argument("--rollouts", type=int, default=100_000)
 ap.add_argument("--batch", type=int, default=8192)
-ap.add_argument("--traj", type=int, default=8, help="SSA trajectories per rollout")
+ap.add_argument("--traj", type=int, default=32, help="SSA trajectories per rollout (a warp runs one topology: multiples of 32 fill it)")
 ap.add_argument("--depth", type=int, default=3, help="reward batches in flight")
 ap.add_argument("--components", default="ABC")
 ap.add_argument("--regulators", default="DE")
@@ -31,7 +31,16 @@ tree.search_mcts_batched(min(256, args.rollouts), 256)                      # wa
 eng = tree.reward_engine
 ev0, tr0, v0 = eng.total_events, eng.total_trajectories, tree.graph.nodes[root]["visits"]
 t0 = time.perf_counter()
-tree.search_mcts_batched(args.rollouts, args.batch, pipeline_depth=args.depth)
+
+
+def progress(t, step, path, sim, reward):
+    if step >= 0 and (step + 1) % args.batch == 0:
+        el = time.perf_counter() - t0
+        print(f"[{el:7.1f}s] {step + 1} rollouts back-propagated, {eng.total_events - ev0:.3e} events, "
+              f"{(eng.total_events - ev0) / max(1, eng.total_trajectories - tr0):.3e} events/trajectory", file=sys.stderr, flush=True)
+
+
+tree.search_mcts_batched(args.rollouts, args.batch, pipeline_depth=args.depth, callback=progress, callback_before_start=False)
 dt = time.perf_counter() - t0
 terminals = [(n, d["reward"] / d["visits"], d["visits"]) for n, d in tree.graph.nodes(data=True)
              if isinstance(n, str) and n.startswith("*") and d["visits"] >= 20]

@@ -212,21 +212,24 @@ def test_get_reward_through_circuitree_api_with_dimers_grammar():
     r_osc = tree.get_reward("*ABC+R::AAiB_BBiC_CCiA")
     r_flat = tree.get_reward("*ABC+R::")
     assert r_osc > 0.55 and r_flat < 0.3
-    tree.search_mcts_batched(64, 32)
-    assert tree.graph.nodes["ABC+R::"]["visits"] == 64
-    assert 0.0 < tree.graph.nodes["ABC+R::"]["reward"] / 64 < 1.0
+    # the search itself on a short grid (random dimer networks fire ~2e6 events per full trajectory)
+    short = OscillationTree(grammar=GRAMMAR, root="ABC+R::", seed=1, n_exhausted=np.inf, trajectories_per_reward=32,
+                            sim_config=small_cfg(nt=320, decim=16))
+    short.search_mcts_batched(64, 32)
+    assert short.graph.nodes["ABC+R::"]["visits"] == 64
+    assert 0.0 < short.graph.nodes["ABC+R::"]["reward"] / 64 < 1.0
 
 
 def test_pipelined_search_with_dimers_grammar():
     """search_mcts_batched(pipeline_depth=3): asynchronous dimer-kernel batches behind the Python tree."""
     def run():
-        c = small_cfg(nt=480, decim=16)
+        c = small_cfg(nt=160, decim=16)
         t = OscillationTree(grammar=GRAMMAR, root="ABC+R::", seed=4, n_exhausted=np.inf, trajectories_per_reward=8, sim_config=c)
-        t.search_mcts_batched(192, 32, pipeline_depth=3)
+        t.search_mcts_batched(96, 16, pipeline_depth=3)
         return t
     a, b = run(), run()
-    assert a.graph.nodes["ABC+R::"]["visits"] == 192
-    assert a.reward_engine.total_trajectories == 192 * 8
-    assert 0.0 < a.graph.nodes["ABC+R::"]["reward"] / 192 < 1.0
+    assert a.graph.nodes["ABC+R::"]["visits"] == 96
+    assert a.reward_engine.total_trajectories == 96 * 8
+    assert 0.0 < a.graph.nodes["ABC+R::"]["reward"] / 96 < 1.0
     assert sorted((n, d["visits"], d["reward"]) for n, d in a.graph.nodes(data=True)) == \
         sorted((n, d["visits"], d["reward"]) for n, d in b.graph.nodes(data=True))
