@@ -150,8 +150,8 @@ def main() -> None:
     ap.add_argument("--cpu-traj", type=int, default=4096, help="trajectories of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mcts-batch", type=int, default=8192, help="leaves per reward launch in the MCTS leg")
-    ap.add_argument("--mcts-batches", type=int, default=6)
-    ap.add_argument("--mcts-depth", type=int, default=3, help="reward batches in flight (virtual loss)")
+    ap.add_argument("--mcts-batches", type=int, default=12)
+    ap.add_argument("--mcts-depth", type=int, default=4, help="reward batches in flight (virtual loss), sharing the device")
     ap.add_argument("--mcts-traj", type=int, default=16, help="SSA trajectories per rollout in the MCTS leg")
     ap.add_argument("--dimer-log2-traj", type=int, default=20, help="trajectories of the dimer-model leg = 2^T (0 = skip)")
     args = ap.parse_args()

@@ -40,6 +40,7 @@ class SimConfig(ctypes.Structure):
         ("init_mean", ctypes.c_float),
         ("schedule", ctypes.c_int32),
         ("lpt", ctypes.c_int32),
+        ("grid_limit", ctypes.c_int32),
         ("fast_path", ctypes.c_int32),
         ("ranges", (ctypes.c_float * 3) * MAX_PARAMS),
     ]

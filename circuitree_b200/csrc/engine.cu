@@ -107,6 +107,7 @@ int validate_cfg(const ct_sim_config* cfg)
     if (!(cfg->init_mean >= 0.0f) || cfg->init_mean > 80.0f) return fail(CT_ERR_INVALID, "init_mean out of range [0, 80]");
     if (cfg->schedule < 0 || cfg->schedule > 2) return fail(CT_ERR_INVALID, "schedule must be 0 (auto), 1 (uniform) or 2 (mixed)");
     if (cfg->lpt < 0 || cfg->lpt > 1) return fail(CT_ERR_INVALID, "lpt must be 0 or 1");
+    if (cfg->grid_limit < 0) return fail(CT_ERR_INVALID, "grid_limit must be >= 0");
     if (cfg->fast_path < 0 || cfg->fast_path > 1) return fail(CT_ERR_INVALID, "fast_path must be 0 or 1");
     return CT_OK;
 }
@@ -132,6 +133,7 @@ int ct_default_config(ct_sim_config* cfg)
     cfg->init_mean = 10.0f;
     cfg->schedule = 0;
     cfg->lpt = 1;
+    cfg->grid_limit = 0;
     cfg->fast_path = 1;
     memcpy(cfg->ranges, r, sizeof r);
     return CT_OK;
@@ -440,7 +442,9 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
         CT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ct::ssa_dimers_kernel, ct::kDimThreads, smem));
         if (per_sm < 1) return fail(CT_ERR_CUDA, "dimer SSA kernel does not fit on an SM (%zu bytes of shared memory)", smem);
         const uint64_t want = (total + ct::kDimThreads - 1) / ct::kDimThreads;
-        const uint64_t cap = (uint64_t)eng->n_sm * per_sm;
+        uint64_t cap = (uint64_t)eng->n_sm * per_sm;
+        if (cfg->grid_limit > 0 && (uint64_t)cfg->grid_limit * (ct::kThreads / ct::kDimThreads) < cap)
+            cap = (uint64_t)cfg->grid_limit * (ct::kThreads / ct::kDimThreads);   // grid_limit counts 128-thread CTAs
         const unsigned dgrid = (unsigned)(want < cap ? want : cap);
         uint8_t* d_records = nullptr;      // per-lane record scratch (see ssa_dimers.cuh)
         CT_CUDA(cudaMallocAsync((void**)&d_records, (size_t)dgrid * ct::kDimThreads * lay.rec_lane_bytes(), stream));
@@ -475,6 +479,7 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
     const KernelInfo& ki = fast ? eng->ki_fast[mm - 3] : eng->ki[mm - 3][mixed ? 1 : 0][all_full ? 1 : 0];
     uint64_t want_blocks = (total + ct::kThreads - 1) / ct::kThreads;
     uint64_t max_blocks = (uint64_t)eng->n_sm * ki.blocks_per_sm;
+    if (cfg->grid_limit > 0 && (uint64_t)cfg->grid_limit < max_blocks) max_blocks = (uint64_t)cfg->grid_limit;
     const unsigned grid = (unsigned)(want_blocks < max_blocks ? want_blocks : max_blocks);
 #define CT_LAUNCH(MM, MIXED, ALL) ct::ssa_pairwise_kernel<MM, MIXED, ALL><<<grid, ct::kThreads, ki.smem, stream>>>(A)
 #define CT_LAUNCH_M(MM)                                                          \

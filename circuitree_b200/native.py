@@ -253,6 +253,8 @@ class NativeTree:
         inflight: deque = deque()
         step = 0        # leaves selected
         done = 0        # leaves back-propagated
+        if self.reward_fn is None:
+            self.reward_engine.share = max(1, int(pipeline_depth))     # batches in flight share the device
 
         def retire():
             nonlocal done
@@ -283,6 +285,8 @@ class NativeTree:
                 retire()
         while inflight:
             retire()
+        if self.reward_fn is None:
+            self.reward_engine.share = 1
 
     def grow_tree(self) -> None:
         _check(_lib().ct_tree_grow(self._h))

@@ -40,6 +40,7 @@ class RewardEngine:
         self.total_events = 0
         self.total_trajectories = 0
         self.cost: dict[int, float] = {}   # topology handle -> events per trajectory observed so far
+        self.share = 1               # asynchronous batches kept in flight: each gets 1/share of the CTA slots
 
     @property
     def engine(self) -> _capi.Engine:
@@ -97,7 +98,15 @@ class RewardEngine:
         offsets = np.concatenate(([0], np.cumsum(n_traj, dtype=np.uint64)[:-1])).astype(np.uint64)
         bases = offsets + np.uint64(self.next_traj)
         self.next_traj += int(n_traj.sum())
-        ticket = self.engine.submit(uniq, n_traj, bases, self.cfg, self.seed, job_cost=job_cost)
+        # batches in flight run side by side, each on its share of the device: a launch that owned every
+        # CTA slot would make the next one wait for its tail (the longest trajectories of the batch)
+        limit = self.cfg.grid_limit
+        if self.share > 1:
+            self.cfg.grid_limit = max(1, -(-(self.engine.resident_lanes // 128) // self.share))
+        try:
+            ticket = self.engine.submit(uniq, n_traj, bases, self.cfg, self.seed, job_cost=job_cost)
+        finally:
+            self.cfg.grid_limit = limit
         return {"ticket": ticket, "uniq": uniq, "inverse": inverse, "n_traj": n_traj, "offsets": offsets,
                 "n_leaves": len(handles), "B": B}
 
@@ -151,6 +160,13 @@ class OscillationTree(CircuiTree):
     def get_rewards(self, states: Sequence[Hashable], **kwargs) -> list[float]:
         out = self._reward_engine.run(list(states), self.trajectories_per_reward)
         return [float(x) for x in out["job_mean"]]
+
+    def search_mcts_batched(self, n_steps: int, batch_size: int, *args, pipeline_depth: int = 1, **kwargs) -> None:
+        self._reward_engine.share = max(1, int(pipeline_depth))
+        try:
+            super().search_mcts_batched(n_steps, batch_size, *args, pipeline_depth=pipeline_depth, **kwargs)
+        finally:
+            self._reward_engine.share = 1
 
     def submit_rewards(self, states: Sequence[Hashable], **kwargs):
         """Asynchronous half of :meth:`get_rewards` (used by ``search_mcts_batched(pipeline_depth > 1)``):

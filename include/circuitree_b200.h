@@ -45,6 +45,9 @@ typedef struct ct_sim_config {
                                 (many small jobs).  Results are identical, only the speed differs. */
     int32_t lpt;             /* 1 (default): start trajectories longest-expected-first (cost pre-pass +
                                 radix sort); 0: in id order.  Results are identical. */
+    int32_t grid_limit;      /* 0 (default): a launch may fill every CTA slot of the device; k > 0: at most k CTAs,
+                                so that several launches submitted on different streams (ct_rewards_submit)
+                                share the device side by side instead of one after the other.  Results are identical. */
     int32_t fast_path;       /* 1 (default): launches whose topologies give every gene at most one regulator
                                 use the specialised hot loop; 0: always the general one.  Results are identical. */
     float ranges[CT_MAX_PARAMS][3]; /* (lo, hi, is_log) per parameter, SPEC.md sections 4 and 9
