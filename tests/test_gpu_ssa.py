@@ -115,6 +115,9 @@ def test_constitutive_expression_level(eng, cfg):
     g = gpu_run(eng, ["*A::"], 256, cfg, seed=5, series=True, params=p)
     level = (g["series"][:, 0, 60:].astype(float) ** 2 / 16).mean()
     assert 235 < level < 265          # km*kp/(gm*gp) = 250
+    # textbook birth-death fluxes: 2 km (1 + kp/gm) = 3.5 events/s once settled (~5/gp = 1000 s of ramp-up)
+    expected = 3.5 * (2000 * 20.0 - 1000.0) + 3.5 * 1000.0 * 0.5
+    assert abs(g["events"].mean() - expected) / expected < 0.02
 
 
 # ---- statistical equivalence, 10^4 trajectories per topology -------------------------------------------

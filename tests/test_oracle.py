@@ -170,3 +170,19 @@ def test_recorded_dimer_results_are_what_the_checker_computes():
         assert np.array_equal(r["reward"], gold[name + "/reward"][:12]), name
         assert np.array_equal(r["lag"], gold[name + "/lag"][:12]), name
         assert np.array_equal(r["n_events"], gold[name + "/n_events"][:12]), name
+
+
+def test_unregulated_gene_matches_birth_death_theory():
+    """An external anchor for the unpinned model: one unregulated gene is the textbook two-stage
+    birth-death process -- stationary means R = km/gm, P = km kp/(gm gp), and 2 km (1 + kp/gm) events
+    per second (each of transcription, mRNA decay, translation, protein decay at its stationary flux)."""
+    km, kp, gm, gp = 0.5, 0.05, 0.02, 0.005
+    p = np.tile([0.01, 0.2, 0.004, km, km, km, km, kp, gm, gp], (96, 1))
+    o = so.run_pairwise(1, [], [], RANGES, 96, seed=8, explicit_params=p, want_series=True, n_threads=so.max_threads())
+    T = 2000 * 20.0
+    relax = 5.0 / gp                                    # the protein level needs ~5/gp = 1000 s to settle
+    level = (o["series"][:, 0, 60:].astype(float) ** 2 / 16).mean()
+    assert abs(level - km * kp / (gm * gp)) / (km * kp / (gm * gp)) < 0.03
+    rate = 2.0 * km * (1.0 + kp / gm)
+    expected = rate * (T - relax) + rate * relax * 0.5  # ramp-up from an (almost) empty cell
+    assert abs(o["n_events"].mean() - expected) / expected < 0.02
