@@ -7,7 +7,9 @@ that it adds the batched scheduler the GPU reward path needs (``get_rewards``,
 ``search_mcts_batched``): K leaves are selected under virtual loss, simulated in one launch,
 then back-propagated -- K = 1 is exactly ``search_mcts``.
 
-Out of scope here: motif statistics, complexity graphs, plotting.
+Sampling of terminal / successful states and the pattern-significance tests (reference
+circuitree.py:1200-1648) live in ``motifs.py`` (``MotifMixin``).  Out of scope here (SURVEY.md
+section 8): complexity graphs, plotting.
 """
 from __future__ import annotations
 
@@ -21,6 +23,7 @@ import networkx as nx
 import numpy as np
 
 from .grammar import CircuitGrammar
+from .motifs import MotifMixin
 
 __all__ = ["ucb_score", "ExhaustionError", "CircuiTree"]
 
@@ -41,7 +44,7 @@ class ExhaustionError(RuntimeError):
     """Every node of the tree has been visited to exhaustion (reference circuitree.py:60)."""
 
 
-class CircuiTree(ABC):
+class CircuiTree(MotifMixin, ABC):
     """Monte Carlo tree search over a :class:`CircuitGrammar`; subclass and implement
     :meth:`get_reward` (reference circuitree.py:64-152)."""
 

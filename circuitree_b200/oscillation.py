@@ -20,7 +20,7 @@ import numpy as np
 from . import _capi
 from .circuitree import CircuiTree
 
-__all__ = ["OscillationTree", "RewardEngine", "reward_landscape"]
+__all__ = ["OscillationTree", "RewardEngine", "reward_landscape", "landscape_motifs"]
 
 
 class RewardEngine:
@@ -209,3 +209,19 @@ def reward_landscape(engine: RewardEngine, states: Sequence[Hashable], n_per_sta
         out["success"][sl] = (r > 0.4).mean(axis=1)
         out["events"][sl] = res["job_events"]
     return out
+
+
+def landscape_motifs(grammar, states: Sequence[Hashable], landscape: dict, patterns: Sequence[str], n_per_state: int,
+                     confidence: Optional[float] = 0.95):
+    """Motif enrichment straight from a reward landscape (:func:`reward_landscape` output): every
+    simulated (topology, parameter set) pair is one sample of the null population, the pairs whose
+    reward exceeded the success threshold are the successful population; each pattern's 2x2 table is
+    tested as in ``CircuiTree.test_pattern_significance`` (reference circuitree.py:1510-1648).
+    Returns the same pandas table, sorted by odds ratio."""
+    from .motifs import pattern_table
+
+    idx = np.asarray(landscape["index"])
+    null = {states[i]: int(n_per_state) for i in idx}
+    succ = {states[i]: int(round(float(f) * n_per_state)) for i, f in zip(idx, landscape["success"])}
+    succ = {s: c for s, c in succ.items() if c > 0}
+    return pattern_table(grammar, patterns, null, succ, confidence=confidence, exclude_self=False)

@@ -9,7 +9,7 @@ simulates n parameter sets per topology on the GPU; prints throughput and the to
 import argparse, json, os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
-from circuitree_b200 import RewardEngine, SimpleNetworkGrammar, reward_landscape
+from circuitree_b200 import RewardEngine, SimpleNetworkGrammar, landscape_motifs, reward_landscape
 from circuitree_b200.native import NativeTree
 
 ap = argparse.ArgumentParser()
@@ -31,8 +31,12 @@ t0 = time.perf_counter()
 res = reward_landscape(eng, terminals, args.n, rank=rank, world=world)
 dt = time.perf_counter() - t0
 best = np.argsort(-res["mean"])[:5]
+# which motifs are enriched among the (topology, parameter set) pairs that oscillate? (this rank's share)
+MOTIFS = ["ABi_BCi_CAi", "ABi_BAi", "AAa", "AAi", "ABa_BAi", "ABa_BCa_CAa", "AAa_ABi_BAi", "ABi_BCi_CAa"]
+motifs = landscape_motifs(grammar, terminals, res, MOTIFS, args.n)
 print(json.dumps({"rank": rank, "world": world, "terminal_states": len(terminals), "enumeration_s": round(t_enum, 3),
                   "states_this_rank": len(res["index"]), "trajectories": len(res["index"]) * args.n,
                   "events": int(res["events"].sum()), "seconds": round(dt, 2),
                   "reaction_steps_per_s": float(res["events"].sum() / dt),
-                  "top": [[terminals[res["index"][i]], round(float(res["mean"][i]), 4), round(float(res["success"][i]), 3)] for i in best]}))
+                  "top": [[terminals[res["index"][i]], round(float(res["mean"][i]), 4), round(float(res["success"][i]), 3)] for i in best],
+                  "motif_odds_ratios": {r["pattern"]: round(float(r["odds_ratio"]), 3) for _, r in motifs.iterrows()}}))
