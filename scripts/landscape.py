@@ -1,7 +1,7 @@
 """BASELINE config 5: reward landscape of every 3-component topology (and, sampled, 4-component ones).
 
     python scripts/landscape.py [--n 10000] [--components 3] [--limit K]
-    torchrun --nproc-per-node 8 scripts/landscape.py --n 10000        # sharded, no collective
+    torchrun --nproc-per-node 8 scripts/landscape.py --param-sets 10000        # sharded, no collective
 
 Enumerates the terminal states natively (ct_tree_grow), shards them round-robin over ranks and
 simulates n parameter sets per topology on the GPU; prints throughput and the top topologies.
@@ -13,7 +13,7 @@ from circuitree_b200 import RewardEngine, SimpleNetworkGrammar, landscape_motifs
 from circuitree_b200.native import NativeTree
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--n", type=int, default=10000)
+ap.add_argument("--n", "--param-sets", dest="n", type=int, default=10000, help="parameter sets per topology (use --param-sets under torchrun: its own parser claims --n)")
 ap.add_argument("--components", type=int, default=3)
 ap.add_argument("--limit", type=int, default=0, help="only the first K terminal states (0 = all)")
 args = ap.parse_args()
