@@ -43,6 +43,12 @@ def i_step(n_reactions: int, n_species: int) -> float:
     return 30.0 + 2.75 * n_reactions + 7.0 * n_species + 13.0
 
 
+def workload_name(log2_traj: int, nt: int = 2000) -> str:
+    """The benchmark workload, named identically by both arms."""
+    return (f"repressilator {REPRESSILATOR}: 2^{log2_traj} trajectories x {nt} grid points per GPU per step, "
+            f"parameters sampled per trajectory (SPEC.md ranges)")
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
 
@@ -131,7 +137,8 @@ def run_reference(args) -> None:
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"repressilator {REPRESSILATOR}, bounded CPU sample: {sample}",
+        "config": {"workload": workload_name(args.log2_traj),
+                   "sample": f"bounded CPU sample of that workload: {sample}",
                    "note": "upstream circuitree ships no SSA; this is the repo's CPU restatement of SPEC.md (oracle/)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -307,8 +314,7 @@ def main() -> None:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": kernel_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"repressilator {REPRESSILATOR}: 2^{args.log2_traj} trajectories x {cfg.nt} grid points "
-                                   f"per GPU per step, parameters sampled per trajectory (SPEC.md ranges)",
+            "config": {"workload": workload_name(args.log2_traj, cfg.nt),
                        "trajectories_per_gpu": n, "l2": "256 MiB buffer written between timed iterations",
                        "sharding": "independent trajectory ids per rank, no data-path collective"},
             "clocks": clocks,

@@ -1,5 +1,5 @@
 """One launch of the dimer kernel (homodimer repressilator, SPEC.md section 9) for ncu / timing.
-usage: prof_dimers.py [log2 n] [nt] [reps]"""
+usage: prof_dimers.py [log2 n] [nt] [reps] [big]   (big = five TFs, ten interactions, ten dimers)"""
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
@@ -12,7 +12,12 @@ reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 eng = _capi.Engine(0)
 cfg = _capi.default_config()
 cfg.nt = nt
-h = _capi.compile_topology(4, [], [(0, 0, 1), (1, 1, 2), (2, 2, 0)], k=3)
+if len(sys.argv) > 4 and sys.argv[4] == "big":
+    # *ABCDE+::AAiB_BBiC_CCiD_DDiE_EEiA_ABaA_BCaB_CDaC_DEaD_AEaE
+    h = _capi.compile_topology(5, [(0, 1, 0), (1, 2, 1), (2, 3, 2), (3, 4, 3), (0, 4, 4)],
+                               [(0, 0, 1), (1, 1, 2), (2, 2, 3), (3, 3, 4), (4, 4, 0)], k=3)
+else:
+    h = _capi.compile_topology(4, [], [(0, 0, 1), (1, 1, 2), (2, 2, 0)], k=3)
 N = 1 << logn
 d_reward = torch.zeros(N, device="cuda")
 d_events = torch.zeros(N, dtype=torch.int32, device="cuda")
