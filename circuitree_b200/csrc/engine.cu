@@ -178,7 +178,13 @@ int ct_engine_create(int device, ct_engine** out)
                                               cudaSharedmemCarveoutMaxShared);
         cudaError_t e3 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.blocks_per_sm, ct::ssa_dimers_kernel,
                                                                        ct::kDimThreads, ki.smem);
-        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || ki.blocks_per_sm < 1) {
+        ct::DimerMixShape big{ct::kMaxSpecies, ct::kMaxIxn, ct::kMaxSpecies * ct::kMixPerTf + 2 * ct::kMaxIxn, 6};
+        cudaError_t e4 = cudaFuncSetAttribute(ct::ssa_dimers_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)(big.warp_bytes() * (ct::kDimThreads / 32)));
+        cudaError_t e5 = cudaFuncSetAttribute(ct::ssa_dimers_mixed_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                              cudaSharedmemCarveoutMaxShared);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess ||
+            ki.blocks_per_sm < 1) {
             delete eng;
             return fail(CT_ERR_CUDA, "dimer SSA kernel does not fit on an SM");
         }
@@ -315,9 +321,13 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
 
     const bool dimers = is_dimer_handle(handles[0]);
     std::vector<ct::DimerProg> progs;   // one reaction program per job (dimer model)
+    std::vector<ct::DimerLaneProg> lane_progs;   // the same topologies as per-lane programs (many small jobs)
+    bool lane_progs_ok = true;          // false: some promoter has more interactions than the per-lane kernel has slots
     ct::DimerLayout lay{1, 1};
+    ct::DimerMixShape shape{1, 0, 0, 0};
     if (dimers) {
         progs.resize((size_t)n_jobs);
+        lane_progs.resize((size_t)n_jobs);
         std::lock_guard<std::mutex> lock(g_dimer_mutex);
         for (int j = 0; j < n_jobs; ++j) {
             const uint64_t idx = handles[j] & 0xffffffffull;
@@ -327,7 +337,12 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
             if (n_traj[j] == 0) continue;
             if (progs[j].n_tf > lay.ser_species) lay.ser_species = progs[j].n_tf;
             if (progs[j].n_entries + 1 > lay.cum_slots) lay.cum_slots = progs[j].n_entries + 1;
+            lane_progs_ok = ct::dimer_lane_program(g_dimer_topos[idx], lane_progs[j]) && lane_progs_ok;
+            if (progs[j].n_tf > shape.n_tf) shape.n_tf = progs[j].n_tf;
+            if (progs[j].n_dim > shape.n_dim) shape.n_dim = progs[j].n_dim;
         }
+        shape.n_entries = shape.n_tf * ct::kMixPerTf + 2 * shape.n_dim;
+        while ((1 << shape.search_iters) < shape.n_entries + 1) ++shape.search_iters;
     }
     std::vector<ct::Job> jobs((size_t)n_jobs);
     uint64_t total = 0, tiles = 0;
@@ -403,7 +418,7 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
         const uint64_t resident = (uint64_t)eng->n_sm * eng->ki[0][0][1].blocks_per_sm * ct::kThreads;
         mixed = n_jobs > 1 && total / (uint64_t)n_jobs < 4 * resident;
     }
-    if (dimers) mixed = false;  // the dimer kernel runs one topology per warp
+    if (dimers && !lane_progs_ok) mixed = false;   // per-lane programs need <= kMixK interactions per promoter
     if (mixed) A.n_tiles = (uint32_t)((total + ct::kTile - 1) / ct::kTile);   // tiles over launch positions
 
     // longest-expected-first order (cfg->lpt): cost pre-pass + radix sort of (job, cost) keys
@@ -434,12 +449,17 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
         A.order = d_order;
     }
     if (dimers) {
-        ct::DimerProg* d_progs = nullptr;
-        CT_CUDA(cudaMallocAsync((void**)&d_progs, sizeof(ct::DimerProg) * progs.size(), stream));
-        CT_CUDA(cudaMemcpyAsync(d_progs, progs.data(), sizeof(ct::DimerProg) * progs.size(), cudaMemcpyHostToDevice, stream));
-        const size_t smem = lay.warp_bytes() * (ct::kDimThreads / 32);
+        // one topology per warp (big jobs) or per-lane programs (many small jobs); identical results
+        void* d_progs = nullptr;
+        const void* h_progs = mixed ? (const void*)lane_progs.data() : (const void*)progs.data();
+        const size_t prog_bytes = mixed ? sizeof(ct::DimerLaneProg) * lane_progs.size() : sizeof(ct::DimerProg) * progs.size();
+        CT_CUDA(cudaMallocAsync(&d_progs, prog_bytes, stream));
+        CT_CUDA(cudaMemcpyAsync(d_progs, h_progs, prog_bytes, cudaMemcpyHostToDevice, stream));
+        const size_t smem = (mixed ? shape.warp_bytes() : lay.warp_bytes()) * (ct::kDimThreads / 32);
+        const size_t rec_lane = mixed ? shape.rec_lane_bytes() : lay.rec_lane_bytes();
         int per_sm = 0;
-        CT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ct::ssa_dimers_kernel, ct::kDimThreads, smem));
+        if (mixed) CT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ct::ssa_dimers_mixed_kernel, ct::kDimThreads, smem));
+        else CT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ct::ssa_dimers_kernel, ct::kDimThreads, smem));
         if (per_sm < 1) return fail(CT_ERR_CUDA, "dimer SSA kernel does not fit on an SM (%zu bytes of shared memory)", smem);
         const uint64_t want = (total + ct::kDimThreads - 1) / ct::kDimThreads;
         uint64_t cap = (uint64_t)eng->n_sm * per_sm;
@@ -447,8 +467,11 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
             cap = (uint64_t)cfg->grid_limit * (ct::kThreads / ct::kDimThreads);   // grid_limit counts 128-thread CTAs
         const unsigned dgrid = (unsigned)(want < cap ? want : cap);
         uint8_t* d_records = nullptr;      // per-lane record scratch (see ssa_dimers.cuh)
-        CT_CUDA(cudaMallocAsync((void**)&d_records, (size_t)dgrid * ct::kDimThreads * lay.rec_lane_bytes(), stream));
-        ct::ssa_dimers_kernel<<<dgrid, ct::kDimThreads, smem, stream>>>(A, d_progs, lay, d_records);
+        CT_CUDA(cudaMallocAsync((void**)&d_records, (size_t)dgrid * ct::kDimThreads * rec_lane, stream));
+        if (mixed)
+            ct::ssa_dimers_mixed_kernel<<<dgrid, ct::kDimThreads, smem, stream>>>(A, (const ct::DimerLaneProg*)d_progs, shape, d_records);
+        else
+            ct::ssa_dimers_kernel<<<dgrid, ct::kDimThreads, smem, stream>>>(A, (const ct::DimerProg*)d_progs, lay, d_records);
         CT_CUDA(cudaGetLastError());
         eng->launches += 1;
         // (pageable host memory: the copy above has been staged when cudaMemcpyAsync returns)

@@ -399,4 +399,323 @@ __global__ void __launch_bounds__(kDimThreads, 10) ssa_dimers_kernel(const Launc
     if (A.warp_iters && lane == 0) atomicAdd(A.warp_iters, (unsigned long long)n_iters);
 }
 
+
+// =====================================================================================================
+// Per-lane programs: the kernel for launches of MANY SMALL dimer jobs (MCTS batches).
+//
+// ssa_dimers_kernel above runs one topology per warp, so a job of 32 trajectories is one warp that
+// waits for its slowest lane before it may change topology; a batch of a thousand distinct
+// topologies then runs at a few percent of the machine.  Here every lane carries its own topology
+// (eight packed words in registers) and lanes are refilled one by one from the launch-wide,
+// longest-first order, exactly like the pairwise kernel's mixed mode.  To keep the warp in
+// lock-step the reaction list has ONE shape for the whole launch: n_tf_max TFs x (4 + 2 K) entries
+// (K = kMixK interaction slots per promoter) followed by 2 entries for each of n_dim_max dimers; what
+// a lane's topology lacks has propensity zero and can never be selected.  Absent entries add an
+// exact 0 to the running sum and the present ones come in SPEC order, so every partial sum, the
+// chosen reaction and therefore every result is bit-identical to ssa_dimers_kernel
+// (tests/test_gpu_dimers.py::test_per_lane_programs_are_bit_identical).  The stoichiometry of entry r
+// follows from r and the lane's packed words; no per-lane table is needed.
+// =====================================================================================================
+constexpr int kMixK = 2;                       // interaction slots per promoter (the DimersGrammar default maximum)
+constexpr int kMixPerTf = 4 + 2 * kMixK;       // 8 entries per TF: power of two, so entry -> (TF, kind) is a shift
+
+struct DimerLaneProg {             // 32 bytes per job
+    uint32_t ixw[kMaxSpecies];     // TF s: interaction slot k at bits 6k: present | activates << 1 | dimer << 2
+    uint32_t dim_a, dim_b;         // monomers of dimer d at bits 3d
+    uint32_t dmask_ntf;            // bit d: dimer d exists; bits 16..19: number of TFs
+};
+
+// false when some promoter has more than kMixK interactions (such launches use ssa_dimers_kernel)
+inline bool dimer_lane_program(const DimerTopo& T, DimerLaneProg& L)
+{
+    memset(&L, 0, sizeof L);
+    for (int s = 0; s < T.n_tf; ++s) {
+        int k = 0;
+        for (int e = 0; e < T.n_ixn; ++e) {
+            if (T.ix_tgt[e] != s) continue;
+            if (k == kMixK) return false;
+            L.ixw[s] |= (1u | ((T.ix_act[e] ? 1u : 0u) << 1) | ((uint32_t)T.ix_dim[e] << 2)) << (6 * k);
+            ++k;
+        }
+    }
+    for (int d = 0; d < T.n_dim; ++d) {
+        L.dim_a |= (uint32_t)T.dim_a[d] << (3 * d);
+        L.dim_b |= (uint32_t)T.dim_b[d] << (3 * d);
+        L.dmask_ntf |= 1u << d;
+    }
+    L.dmask_ntf |= (uint32_t)T.n_tf << 16;
+    return true;
+}
+
+struct DimerMixShape {             // launch-wide shape of the reaction list
+    int32_t n_tf, n_dim;           // maxima over the launch's jobs
+    int32_t n_entries;             // n_tf * kMixPerTf + 2 * n_dim
+    int32_t search_iters;          // ceil(log2(n_entries + 1))
+    __host__ __device__ size_t rec_lane_bytes() const { return (size_t)n_tf * kSerStride; }
+    __host__ __device__ size_t warp_bytes() const
+    {
+        return (size_t)(kSlots + n_entries + 1) * 32 * sizeof(float) + kSerStride * sizeof(float) +
+               (size_t)kMaxSpecies * kSerStride;      // state | running sums | reward scratch | staged record
+    }
+};
+
+__global__ void __launch_bounds__(kDimThreads, 8) ssa_dimers_mixed_kernel(const LaunchArgs A, const DimerLaneProg* __restrict__ lprogs,
+                                                                          const DimerMixShape shape, uint8_t* __restrict__ records)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint8_t* wbase = smem + (size_t)warp * shape.warp_bytes();
+    float* X = reinterpret_cast<float*>(wbase) + lane;        // slot s of this lane: X[s * 32]
+    float* cum = X + kSlots * 32;                             // partial sum r of this lane: cum[r * 32]
+    float* z = reinterpret_cast<float*>(wbase) + (kSlots + shape.n_entries + 1) * 32;
+    uint8_t* stage = reinterpret_cast<uint8_t*>(z + kSerStride);
+    const size_t ser_lane_bytes = shape.rec_lane_bytes();
+    uint8_t* warp_ser = records + ((size_t)blockIdx.x * (kDimThreads / 32) + warp) * 32 * ser_lane_bytes;
+    uint8_t* ser = warp_ser + (size_t)lane * ser_lane_bytes;
+    const int ntf_max = shape.n_tf, nd_max = shape.n_dim, n_entries = shape.n_entries, search_iters = shape.search_iters;
+    const int tf_entries = ntf_max * kMixPerTf;
+
+    float k_on = 0.f, k_on2 = 0.f, k_off1 = 0.f, k_off2 = 0.f, km0 = 0.f, km1 = 0.f, km2 = 0.f, km3 = 0.f, kp = 0.f, gm = 0.f,
+          gp = 0.f, k_dim = 0.f, k_undim = 0.f;
+    float t_rem = 0.0f;
+    int k = 0, kd = 0, dcount = 1;
+    uint32_t events = 0, ctr = 0, traj_lo = 0, traj_hi = 0, out = 0;
+    bool active = false, finished = false;
+    // this lane's topology (a parked lane: no TFs, no dimers)
+    uint32_t ixw[kMaxSpecies] = {0u, 0u, 0u, 0u, 0u};
+    uint32_t dma = 0, dmb = 0, dmask = 0;
+    int n_tf = 0;
+#pragma unroll 1
+    for (int s = 0; s < kSlots; ++s) X[s * 32] = 0.0f;
+    cum[n_entries * 32] = 3.4e38f;        // sentinel: "no reaction" is always found
+
+    uint32_t pos = 0, end = 0;            // launch positions of the warp's current tile
+    bool out_of_work = false;
+    uint32_t n_iters = 0;
+
+    for (;;) {
+        const unsigned idle = __ballot_sync(kFull, !active);
+        if (idle) {
+            // 1. reduce finished trajectories to (reward, lag), one lane at a time, whole warp helping
+            unsigned fin = __ballot_sync(kFull, finished);
+            if (fin) __syncwarp();
+            while (fin) {
+                const int src = __ffs(fin) - 1;
+                fin &= fin - 1;
+                float rw; int lg;
+                const int src_ntf = __shfl_sync(kFull, n_tf, src);
+                const uint32_t* grec = reinterpret_cast<const uint32_t*>(warp_ser + (size_t)src * ser_lane_bytes);
+                for (int w = lane; w < src_ntf * (kSerStride / 4); w += 32) reinterpret_cast<uint32_t*>(stage)[w] = __ldcg(grec + w);
+                __syncwarp();
+                warp_reward(stage, z, src_ntf, A.n_dec, lane, rw, lg);
+                const uint32_t o = __shfl_sync(kFull, out, src);
+                if (A.series) {
+                    for (int s = 0; s < src_ntf; ++s)
+                        for (int q = lane; q < A.n_dec; q += 32)
+                            A.series[(size_t)o * A.series_stride + s * A.n_dec + q] = stage[s * kSerStride + q];
+                }
+                __syncwarp();
+                if (lane == src) {
+                    A.reward[o] = rw;
+                    if (A.lag) A.lag[o] = lg;
+                    if (A.events) A.events[o] = events;
+                    finished = false;
+                }
+            }
+            // 2. refill idle lanes from the launch-wide order (tiles are ranges of launch positions)
+            unsigned need = idle;
+            for (;;) {
+                if (pos < end) {
+                    const int rank = __popc(need & ((1u << lane) - 1u));
+                    const uint32_t avail = end - pos;
+                    const bool take = !active && (uint32_t)rank < avail;
+                    if (take) {
+                        const uint32_t slot = A.order ? A.order[pos + rank] : pos + rank;
+                        const uint32_t jx = job_of_slot(A, slot);
+                        const Job mine = A.jobs[jx];
+                        const DimerLaneProg P = lprogs[jx];
+#pragma unroll
+                        for (int s = 0; s < kMaxSpecies; ++s) ixw[s] = P.ixw[s];
+                        dma = P.dim_a; dmb = P.dim_b; dmask = P.dmask_ntf & 0x3ffu; n_tf = (int)(P.dmask_ntf >> 16) & 15;
+                        const uint64_t traj = mine.traj_base + (slot - mine.out_offset);
+                        traj_lo = (uint32_t)traj; traj_hi = (uint32_t)(traj >> 32);
+                        out = slot;
+                        float prm[12];
+                        trajectory_params(A, traj_lo, traj_hi, slot, prm);
+                        k_on = prm[0]; k_on2 = 2.0f * prm[0]; k_off1 = prm[1]; k_off2 = prm[2];
+                        km0 = prm[3]; km1 = prm[4]; km2 = prm[5]; km3 = prm[6];
+                        kp = prm[7]; gm = prm[8]; gp = prm[9]; k_dim = prm[10]; k_undim = prm[11];
+#pragma unroll 1
+                        for (int s = 0; s < kSlots; ++s) X[s * 32] = 0.0f;
+                        const float e0 = expf(-A.init_mean);
+#pragma unroll 1
+                        for (int blk4 = 0; blk4 < 2; ++blk4) {
+                            const Philox4 x = philox4x32_10(3 + blk4, 0u, traj_lo, traj_hi, A.seed_lo, A.seed_hi);
+#pragma unroll
+                            for (int w = 0; w < 4; ++w) {
+                                const int s = 4 * blk4 + w;
+                                if (s < n_tf) {
+                                    const float u = u01(x.w[w]);
+                                    float pk = e0, F = e0;
+                                    int kk = 0;
+                                    while (u > F && kk < 1000) { ++kk; pk *= A.init_mean / (float)kk; F += pk; }
+                                    X[(kSlotP + s) * 32] = (float)kk;
+                                }
+                            }
+                        }
+                        t_rem = 0.0f;
+                        k = 0; kd = 0; dcount = A.decim;
+                        events = 0; ctr = 0;
+                        active = true;
+                    }
+                    const uint32_t n_need = __popc(need);
+                    pos += (n_need < avail) ? n_need : avail;
+                    need = __ballot_sync(kFull, !active);
+                    if (!need) break;
+                }
+                if (out_of_work) break;
+                uint32_t t = 0;
+                if (lane == 0) t = atomicAdd(A.tile_counter, 1u);
+                t = __shfl_sync(kFull, t, 0);
+                if (t >= A.n_tiles) { out_of_work = true; break; }
+                pos = t * kTile;
+                end = min(pos + (uint32_t)kTile, A.total);
+            }
+            if (out_of_work && __ballot_sync(kFull, active) == 0u) break;
+        }
+        ++n_iters;
+
+        const Philox4 x = philox4x32_10_rk(ctr, 1u, traj_lo, traj_hi, A.rk);
+        ctr += 1;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t w_tau = h ? x.w[2] : x.w[0], w_sel = h ? x.w[3] : x.w[1];
+            // ---- pass 1: the launch-wide reaction list; what this lane's topology lacks contributes an exact 0 ----
+            float c = 0.0f;
+            float* cp = cum;
+#pragma unroll
+            for (int s = 0; s < kMaxSpecies; ++s) {
+                if (s < ntf_max) {       // warp-uniform (launch constant)
+                    const float n = X[(kSlotN + s) * 32], na = X[(kSlotA + s) * 32];
+                    const float r = X[(kSlotR + s) * 32], p = X[(kSlotP + s) * 32];
+                    const float km_a = (na > 0.0f) ? km1 : km0;
+                    const float km_i = (na > 0.0f) ? km3 : km2;
+                    const float km = (n > na) ? km_i : km_a;
+                    c += (s < n_tf) ? km : 0.0f;    cp[0] = c;      // (a TF this lane does not have: no transcription)
+                    c = fmaf(gm, r, c);             cp[32] = c;
+                    c = fmaf(kp, r, c);             cp[64] = c;
+                    c = fmaf(gp, p, c);             cp[96] = c;
+                    const float kfree = fmaf(-k_on, n, k_on2);            // k_on (2 - n)
+                    const float koff = (n >= 2.0f) ? k_off2 : k_off1;
+                    const uint32_t iw = ixw[s];
+#pragma unroll
+                    for (int q = 0; q < kMixK; ++q) {
+                        const uint32_t f = iw >> (6 * q);
+                        const float dv = X[(kSlotD + ((f >> 2) & 15u)) * 32];
+                        c = fmaf((f & 1u) ? kfree : 0.0f, dv, c);       cp[(4 + q) * 32] = c;
+                    }
+#pragma unroll
+                    for (int q = 0; q < kMixK; ++q) {
+                        c = fmaf(koff, X[(kSlotB + kMixK * s + q) * 32], c);    cp[(4 + kMixK + q) * 32] = c;
+                    }
+                    cp += kMixPerTf * 32;
+                }
+            }
+#pragma unroll 1
+            for (int d = 0; d < nd_max; ++d) {
+                const uint32_t da = (dma >> (3 * d)) & 7u, db = (dmb >> (3 * d)) & 7u;
+                const float pa = X[(kSlotP + da) * 32], pb = X[(kSlotP + db) * 32];
+                const float pairs = (da != db) ? pa * pb : 0.5f * pa * (pa - 1.0f);
+                c = fmaf(((dmask >> d) & 1u) ? k_dim : 0.0f, pairs, c);     cp[0] = c;
+                c = fmaf(k_undim, X[(kSlotD + d) * 32], c);                  cp[32] = c;
+                cp += 64;
+            }
+            const float a0 = c;
+
+            // ---- time to next event; grid samples crossed keep the pre-event state ----
+            const float tau = (-0.69314718056f * fast_log2(u01(w_tau))) * fast_rcp(a0);   // a0 == 0 -> +inf
+            t_rem -= tau;
+            bool alive = true;
+            const bool was_active = active;
+            if (active && t_rem < 0.0f) {
+                do {
+#pragma unroll
+                    for (int s = 0; s < kMaxSpecies; ++s)
+                        if (s < n_tf) X[(kSlotBlk + s) * 32] += fminf(X[(kSlotP + s) * 32], kSampleCap);
+                    k += 1;
+                    if (--dcount == 0) {
+                        dcount = A.decim;
+#pragma unroll 1
+                        for (int s = 0; s < n_tf; ++s) {
+                            ser[s * kSerStride + kd] = (uint8_t)compand_block(X[(kSlotBlk + s) * 32]);
+                            X[(kSlotBlk + s) * 32] = 0.0f;
+                        }
+                        kd += 1;
+                    }
+                    t_rem += A.dt;
+                } while (t_rem < 0.0f && k < A.nt);
+                if (k >= A.nt) { alive = false; active = false; finished = true; }
+            }
+
+            // ---- pass 2: find the reaction (first partial sum above the target), derive its stoichiometry, fire ----
+            const float target = alive ? u01(w_sel) * a0 : 3.0e38f;
+            int lo = 0, hi = n_entries;
+#pragma unroll 1
+            for (int it = 0; it < search_iters; ++it) {
+                const int mid = (lo + hi) >> 1;
+                const bool lt = target < cum[mid * 32];
+                hi = lt ? mid : hi;
+                lo = lt ? lo : mid + 1;
+            }
+            // four (slot, delta) fields on distinct slots; unused fields sit on the four dummies
+            int s0 = kSlotDummy, s1 = kSlotDummy + 1, s2 = kSlotDummy + 2, s3 = kSlotDummy + 3;
+            float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+            if (lo < tf_entries) {
+                const int s = lo >> 3, w = lo & 7;
+                static_assert(kMixPerTf == 8 && kMixK == 2, "entry -> (TF, kind) decoding assumes 8 entries per TF");
+                if (w < 4) {        // transcription, mRNA decay, translation, monomer decay
+                    s0 = ((w & 2) ? kSlotP : kSlotR) + s;
+                    d0 = (w & 1) ? -1.0f : 1.0f;
+                } else {            // binding (w = 4, 5) / unbinding (w = 6, 7) of interaction slot q at promoter s
+                    const int q = w & 1;
+                    const float sg = (w >= 6) ? -1.0f : 1.0f;
+                    uint32_t iw = ixw[0];
+#pragma unroll
+                    for (int j = 1; j < kMaxSpecies; ++j) iw = (s == j) ? ixw[j] : iw;
+                    const uint32_t f = iw >> (6 * q);
+                    s0 = kSlotD + (int)((f >> 2) & 15u);    d0 = -sg;
+                    s1 = kSlotB + kMixK * s + q;            d1 = sg;
+                    s2 = kSlotN + s;                        d2 = sg;
+                    if (f & 2u) { s3 = kSlotA + s;          d3 = sg; }
+                }
+            } else if (lo < n_entries) {     // dimerisation (even) / dissociation (odd) of dimer d
+                const int j = lo - tf_entries, d = j >> 1;
+                const float sg = (j & 1) ? 1.0f : -1.0f;        // what happens to the monomers
+                const int da = (int)((dma >> (3 * d)) & 7u), db = (int)((dmb >> (3 * d)) & 7u);
+                s0 = kSlotP + da;   d0 = (da == db) ? 2.0f * sg : sg;
+                if (da != db) { s1 = kSlotP + db;   d1 = sg; }
+                s2 = kSlotD + d;    d2 = -sg;
+            }
+            float* f0 = X + s0 * 32;
+            float* f1 = X + s1 * 32;
+            float* f2 = X + s2 * 32;
+            float* f3 = X + s3 * 32;
+            const float v0 = *f0, v1 = *f1, v2 = *f2, v3 = *f3;
+            *f0 = v0 + d0;
+            *f1 = v1 + d1;
+            *f2 = v2 + d2;
+            *f3 = v3 + d3;
+            events += (was_active && alive) ? 1u : 0u;
+            if (!alive) {   // park: zero rates, state and topology so that the lane idles through the lock-step loop
+                k_on = k_on2 = k_off1 = k_off2 = km0 = km1 = km2 = km3 = kp = gm = gp = k_dim = k_undim = 0.0f;
+#pragma unroll 1
+                for (int s = 0; s < kSlots; ++s) X[s * 32] = 0.0f;
+                t_rem = 0.0f;
+            }
+        }
+    }
+    if (A.warp_iters && lane == 0) atomicAdd(A.warp_iters, (unsigned long long)n_iters);
+}
+
 }  // namespace ct

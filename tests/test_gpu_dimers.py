@@ -193,6 +193,28 @@ def test_launch_shape_independence_and_mixed_batches(eng):
         assert np.array_equal(mixed[k], plain[k])
 
 
+def test_per_lane_programs_are_bit_identical(eng):
+    """Launches of many small jobs give every lane its own topology (ssa_dimers_mixed_kernel, schedule 2
+    or automatic); big jobs run one topology per warp (ssa_dimers_kernel, schedule 1).  Same bits."""
+    g5 = DimersGrammar(components=list("ABCDE"), regulators=[], interactions=AI)
+    cases = [
+        (GRAMMAR, TOPOLOGIES + ["*ABC+R::AAaA_BRiA_ABiC", "*ABC+R::CCaB"], [96, 40, 33, 64, 50, 7]),
+        (g5, ["*ABCDE+::AAiB_BBiC_CCiD_DDiE_EEiA_ABaA_BCaB_CDaC_DEaD_AEaE", "*ABCDE+::AEaC", "*ABCDE+::"], [64, 30, 9]),
+        # three interactions on promoter A: more than the per-lane kernel has slots -> it falls back, still equal
+        (GRAMMAR, ["*ABC+R::AAaA_BBiA_CCiA_ABiB", "*ABC+R::AAiB"], [40, 24]),
+    ]
+    for grammar, states, counts in cases:
+        outs = []
+        for schedule in (1, 2, 0):
+            c = small_cfg(nt=400, decim=16)
+            c.schedule = schedule
+            outs.append(gpu_run(eng, states, counts, c, seed=23, bases=np.arange(len(states)) * 1000, grammar=grammar, series=True))
+        for key in ("reward", "lag", "events", "series"):
+            assert np.array_equal(outs[0][key], outs[1][key]), (states[0], key)
+            assert np.array_equal(outs[0][key], outs[2][key]), (states[0], key)
+        assert outs[0]["events"].sum() > 0
+
+
 def test_one_model_per_launch(eng):
     c = small_cfg(nt=160, decim=16)
     pair = _capi.compile_topology(3, [], [(0, 1), (1, 2), (2, 0)])
