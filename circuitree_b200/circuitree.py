@@ -82,7 +82,8 @@ class CircuiTree(MotifMixin, ABC):
         self.grammar = grammar
         self.exploration_constant = np.sqrt(2) if exploration_constant is None else exploration_constant
         self.n_exhausted = n_exhausted
-        self._non_serializable_attrs = ["_non_serializable_attrs", "rg", "graph"]
+        self._non_serializable_attrs = ["_non_serializable_attrs", "rg", "graph", "_child_memo"]
+        self._child_memo: dict = {}        # (state, action) -> child state: the tree revisits the same edges all the time
 
     # ---------------------------------------------------------------------------------------------
     # reward plug-in boundary
@@ -110,6 +111,23 @@ class CircuiTree(MotifMixin, ABC):
     def _do_action(self, state: Hashable, action: Hashable) -> Hashable:
         nxt = self.grammar.do_action(state, action)
         return self.grammar.get_unique_state(nxt) if self.compute_unique else nxt
+
+    _CHILD_MEMO_MAX = 1 << 20
+
+    def _child(self, state: Hashable, action: Hashable) -> Hashable:
+        """``_do_action`` memoised per (state, action): a pure function of the grammar, evaluated
+        for every child of every node on every selection path."""
+        key = (state, action)
+        try:
+            return self._child_memo[key]
+        except KeyError:
+            pass
+        except TypeError:          # unhashable state or action
+            return self._do_action(state, action)
+        if len(self._child_memo) >= self._CHILD_MEMO_MAX:
+            self._child_memo.clear()
+        child = self._child_memo[key] = self._do_action(state, action)
+        return child
 
     def _undo_action(self, state: Hashable, action: Hashable) -> Hashable:
         if state == self.root:
@@ -144,17 +162,34 @@ class CircuiTree(MotifMixin, ABC):
         ``TypeError`` on reaching a terminal node in that case."""
         rg = self.rg if rg is None else rg
         track_exhaustion = self.n_exhausted is not None
+        # fast path: the stock UCB read straight off networkx's adjacency dicts (same arithmetic, same
+        # numpy scalar functions as ucb_score; skipped when a subclass overrides the scoring or _do_action)
+        stock = type(self).get_ucb_score is CircuiTree.get_ucb_score and type(self)._do_action is CircuiTree._do_action
+        adj, nodes, c_explore = self.graph._adj, self.graph._node, self.exploration_constant
+        child_of = self._child if stock else self._do_action
         node = self.root
         path = [node]
         actions = self.grammar.get_actions(node)
         while actions:
             rg.shuffle(actions)
             best, best_score = None, -np.inf
+            out_edges = adj.get(node, {}) if stock else None
+            log_n = None
             for action in actions:
-                child = self._do_action(node, action)
+                child = child_of(node, action)
                 if track_exhaustion and self._is_exhausted(child):
                     continue
-                score = self.get_ucb_score(node, child)
+                if stock:
+                    edge = out_edges.get(child)
+                    if edge is None or edge["visits"] == 0:
+                        score = np.inf
+                    else:
+                        if log_n is None:
+                            log_n = np.log(nodes[node]["visits"])
+                        n = edge["visits"]
+                        score = edge["reward"] / n + c_explore * np.sqrt(log_n / n)
+                else:
+                    score = self.get_ucb_score(node, child)
                 if score == np.inf:
                     self.expand_edge(node, child)
                     path.append(child)
