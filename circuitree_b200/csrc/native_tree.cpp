@@ -121,6 +121,8 @@ struct Edge {
     double reward = 0.0;
     int64_t sync_visits = 0;
     double sync_reward = 0.0;
+    int64_t unc_visits = 0;                 // part of (visits, reward) already un-counted from the parent
+    double unc_reward = 0.0;                // because the child is flagged exhausted (root-parallel replicas)
 };
 
 }  // namespace
@@ -146,6 +148,8 @@ struct ct_tree {
     std::vector<std::vector<int>> pending;   // paths (node ids) awaiting rewards, FIFO
     size_t pending_head = 0;
     bool exhausted_all = false;
+    std::vector<uint64_t> newly_exhausted;   // keys flagged by this replica since the last delta collection
+    std::vector<int> exhausted_nodes;        // every flagged node, in flagging order
 
     int shift(int cell) const { return 2 * (n_cells - 1 - cell); }
     uint32_t cell(uint64_t key, int c) const { return (uint32_t)(key >> shift(c)) & 3u; }
@@ -239,23 +243,63 @@ struct ct_tree {
     }
 
     // returns false when the whole tree is exhausted (the reference raises ExhaustionError)
-    bool mark_exhausted(int node)
+    // Root-parallel replicas (ct_tree_pack_deltas / ct_tree_merge_packed): the un-counting below is a
+    // consequence of the exhaustion EVENT, which every replica replays for itself; it must not travel
+    // as a statistic increment as well, so the sync baseline moves with it.  `record` is false only
+    // for the node another replica's event names (nodes flagged by the recursion are always recorded:
+    // receivers skip what they have flagged already).
+    bool mark_exhausted(int node, bool record = true)
     {
         nodes[node].exhausted = true;
+        exhausted_nodes.push_back(node);
+        if (record) newly_exhausted.push_back(nodes[node].key);
         if (nodes[node].key == root_key) { exhausted_all = true; return false; }
         for (int e : nodes[node].in_edges) {
             Node& p = nodes[edges[e].parent];
             p.visits -= edges[e].visits;
             p.reward -= edges[e].reward;
+            p.sync_visits -= edges[e].visits;
+            p.sync_reward -= edges[e].reward;
+            edges[e].unc_visits = edges[e].visits;
+            edges[e].unc_reward = edges[e].reward;
         }
         for (size_t x = 0; x < nodes[node].in_edges.size(); ++x) {
             const int parent = edges[nodes[node].in_edges[x]].parent;
             bool all = true;
             for (int e : nodes[parent].out_edges)
                 if (!nodes[edges[e].child].exhausted) { all = false; break; }
-            if (all && !mark_exhausted(parent)) return false;
+            if (all && !nodes[parent].exhausted && !mark_exhausted(parent)) return false;
         }
         return true;
+    }
+
+    // Root-parallel replicas only (never called by a single tree, which follows the reference to the
+    // letter): whatever reached an edge into a flagged node after the node was flagged -- the
+    // flagging traversal's own visit and reward, rewards of leaves that were in flight, other
+    // replicas' increments merged later -- is un-counted from the parent too.  Every replica then
+    // holds, for every parent, the sum of all increments minus everything that came through flagged
+    // children, whichever replica did the flagging and whenever the increments arrived.
+    void settle_exhausted()
+    {
+        for (int node : exhausted_nodes)
+            for (int e : nodes[node].in_edges) {
+                Edge& ed = edges[e];
+                if (ed.visits == ed.unc_visits && ed.reward == ed.unc_reward) continue;
+                Node& p = nodes[ed.parent];
+                const int64_t dv = ed.visits - ed.unc_visits;
+                const double dr = ed.reward - ed.unc_reward;
+                p.visits -= dv; p.sync_visits -= dv;
+                p.reward -= dr; p.sync_reward -= dr;
+                ed.unc_visits = ed.visits; ed.unc_reward = ed.reward;
+            }
+    }
+
+    // number of interactions of a state (+1 for a terminal state): its depth below the root
+    int depth_of(uint64_t key) const
+    {
+        int d = (key & kTerminalBit) ? 1 : 0;
+        for (int c = 0; c < n_cells; ++c) d += cell(key, c) != 3u;
+        return d;
     }
 
     // 0 ok, 1 tree exhausted, 2 dead end (every child exhausted or NaN scores: the reference crashes here)
@@ -488,6 +532,7 @@ int ct_tree_select(ct_tree* t, int32_t k, uint64_t* sim_keys, uint64_t* sim_hand
     *n_done = 0;
     std::vector<int> path;
     for (int x = 0; x < k; ++x) {
+        if (t->exhausted_all) return tfail(100, "ExhaustionError: every node in the tree has been visited to exhaustion");
         const int rc = t->select_and_expand(path);
         if (rc == 1) return tfail(100, "ExhaustionError: every node in the tree has been visited to exhaustion");
         if (rc == 2) return tfail(CT_ERR_INVALID, "selection reached a node without selectable children");
@@ -628,60 +673,101 @@ int ct_tree_grow(ct_tree* t)
     return CT_OK;
 }
 
-/* Multi-GPU root-parallel merge, step 1: changes of (visits, reward) since the previous call, as
- * sparse records keyed by packed state.  Call with NULL arrays to get the counts. */
-int ct_tree_collect_deltas(ct_tree* t, int64_t* n_node_recs, uint64_t* node_key, int64_t* node_dv, double* node_dr,
-                           int64_t* n_edge_recs, uint64_t* edge_pkey, uint64_t* edge_ckey, int64_t* edge_dv, double* edge_dr)
+/* Multi-GPU root-parallel merge, step 1: everything this replica has to tell the others since the
+ * previous successful call, as ONE buffer of 64-bit words:
+ *   [0] kPackMagic  [1] n_node  [2] n_edge  [3] n_exhausted  [4] flags (bit 0: whole tree exhausted)
+ *   node keys[n_node] | node d visits[n_node] | node d reward[n_node] (double bits)
+ *   edge parent keys[n_edge] | edge child keys[n_edge] | edge d visits[n_edge] | edge d reward[n_edge]
+ *   keys of nodes flagged exhausted[n_exhausted]
+ * Records are sparse (only what changed) and keyed by packed state: 5-component spaces cannot be
+ * indexed densely.  max_depth >= 0 restricts the exchange to states with at most that many
+ * interactions (+1 for terminal states); -1 exchanges everything.  If buf is NULL or cap is too
+ * small nothing is committed and *n_words is the size needed.  The statistics un-counted by
+ * exhaustion (reference circuitree.py:386-420) never travel as increments: the exhaustion event does,
+ * and every replica replays it (see settle_exhausted). */
+constexpr int64_t kPackMagic = 0x4354444c54413032ll;   // "CTDLTA02"
+constexpr int64_t kPackHeader = 5;
+
+int ct_tree_pack_deltas(ct_tree* t, int32_t max_depth, int64_t* buf, int64_t cap, int64_t* n_words)
 {
-    if (!t || !n_node_recs || !n_edge_recs) return tfail(CT_ERR_INVALID, "NULL argument");
-    const bool fill = node_key != nullptr;
+    if (!t || !n_words) return tfail(CT_ERR_INVALID, "NULL argument");
+    if (t->track_exhaustion) t->settle_exhausted();
+    auto wanted = [&](uint64_t key) { return max_depth < 0 || t->depth_of(key) <= max_depth; };
     int64_t nn = 0, ne = 0;
+    for (const auto& nd : t->nodes)
+        if ((nd.visits != nd.sync_visits || nd.reward != nd.sync_reward) && wanted(nd.key)) ++nn;
+    for (const auto& e : t->edges)
+        if ((e.visits != e.sync_visits || e.reward != e.sync_reward) && wanted(t->nodes[e.child].key)) ++ne;
+    const int64_t nx = (int64_t)t->newly_exhausted.size();
+    const int64_t need = kPackHeader + 3 * nn + 4 * ne + nx;
+    *n_words = need;
+    if (!buf || cap < need) return CT_OK;
+    buf[0] = kPackMagic; buf[1] = nn; buf[2] = ne; buf[3] = nx; buf[4] = t->exhausted_all ? 1 : 0;
+    int64_t* nk = buf + kPackHeader; int64_t* nv = nk + nn; int64_t* nr = nv + nn;
+    int64_t* ep = nr + nn; int64_t* ec = ep + ne; int64_t* ev = ec + ne; int64_t* er = ev + ne; int64_t* xk = er + ne;
+    int64_t a = 0, b = 0;
     for (auto& nd : t->nodes) {
-        if (nd.visits == nd.sync_visits && nd.reward == nd.sync_reward) continue;
-        if (fill) {
-            node_key[nn] = nd.key; node_dv[nn] = nd.visits - nd.sync_visits; node_dr[nn] = nd.reward - nd.sync_reward;
-            nd.sync_visits = nd.visits; nd.sync_reward = nd.reward;
-        }
-        ++nn;
+        if ((nd.visits == nd.sync_visits && nd.reward == nd.sync_reward) || !wanted(nd.key)) continue;
+        const double dr = nd.reward - nd.sync_reward;
+        nk[a] = (int64_t)nd.key; nv[a] = nd.visits - nd.sync_visits; memcpy(&nr[a], &dr, 8);
+        nd.sync_visits = nd.visits; nd.sync_reward = nd.reward;
+        ++a;
     }
     for (auto& e : t->edges) {
-        if (e.visits == e.sync_visits && e.reward == e.sync_reward) continue;   // incl. expanded-but-unvisited edges
-        if (fill) {
-            edge_pkey[ne] = t->nodes[e.parent].key; edge_ckey[ne] = t->nodes[e.child].key;
-            edge_dv[ne] = e.visits - e.sync_visits; edge_dr[ne] = e.reward - e.sync_reward;
-            e.sync_visits = e.visits; e.sync_reward = e.reward;
-        }
-        ++ne;
+        if ((e.visits == e.sync_visits && e.reward == e.sync_reward) || !wanted(t->nodes[e.child].key)) continue;
+        const double dr = e.reward - e.sync_reward;
+        ep[b] = (int64_t)t->nodes[e.parent].key; ec[b] = (int64_t)t->nodes[e.child].key;
+        ev[b] = e.visits - e.sync_visits; memcpy(&er[b], &dr, 8);
+        e.sync_visits = e.visits; e.sync_reward = e.reward;
+        ++b;
     }
-    *n_node_recs = nn;
-    *n_edge_recs = ne;
+    for (int64_t x = 0; x < nx; ++x) xk[x] = (int64_t)t->newly_exhausted[(size_t)x];
+    t->newly_exhausted.clear();
     return CT_OK;
 }
 
-/* Step 2: add other ranks' records (nodes and edges are created as needed).  Merged statistics are
- * the sums of all ranks' increments -- what one tree would hold had it executed every path. */
-int ct_tree_merge_deltas(ct_tree* t, int64_t n_node_recs, const uint64_t* node_key, const int64_t* node_dv, const double* node_dr,
-                         int64_t n_edge_recs, const uint64_t* edge_pkey, const uint64_t* edge_ckey, const int64_t* edge_dv,
-                         const double* edge_dr)
+/* Step 2: add another replica's buffer (nodes and edges are created as needed), then replay its
+ * exhaustion events.  Merged statistics are the sums of all replicas' increments -- what one tree
+ * would hold had it executed every path.  *tree_exhausted (nullable) is set when the root is flagged. */
+int ct_tree_merge_packed(ct_tree* t, const int64_t* buf, int64_t n_words, int32_t* tree_exhausted)
 {
-    if (!t) return tfail(CT_ERR_INVALID, "NULL tree");
-    for (int64_t x = 0; x < n_node_recs; ++x) {
-        int id = t->node_of(node_key[x]);
-        if (id < 0) id = t->add_node(node_key[x]);
+    if (!t || !buf) return tfail(CT_ERR_INVALID, "NULL argument");
+    if (n_words < kPackHeader || buf[0] != kPackMagic) return tfail(CT_ERR_INVALID, "not a delta buffer");
+    const int64_t nn = buf[1], ne = buf[2], nx = buf[3];
+    if (nn < 0 || ne < 0 || nx < 0 || kPackHeader + 3 * nn + 4 * ne + nx > n_words)
+        return tfail(CT_ERR_INVALID, "truncated delta buffer");
+    const int64_t* nk = buf + kPackHeader; const int64_t* nv = nk + nn; const int64_t* nr = nv + nn;
+    const int64_t* ep = nr + nn; const int64_t* ec = ep + ne; const int64_t* ev = ec + ne; const int64_t* er = ev + ne;
+    const int64_t* xk = er + ne;
+    for (int64_t x = 0; x < nn; ++x) {
+        int id = t->node_of((uint64_t)nk[x]);
+        if (id < 0) id = t->add_node((uint64_t)nk[x]);
+        double dr; memcpy(&dr, &nr[x], 8);
         Node& nd = t->nodes[id];
-        nd.visits += node_dv[x]; nd.reward += node_dr[x];
-        nd.sync_visits += node_dv[x]; nd.sync_reward += node_dr[x];
+        nd.visits += nv[x]; nd.reward += dr;
+        nd.sync_visits += nv[x]; nd.sync_reward += dr;
     }
-    for (int64_t x = 0; x < n_edge_recs; ++x) {
-        int p = t->node_of(edge_pkey[x]), c = t->node_of(edge_ckey[x]);
-        if (p < 0) p = t->add_node(edge_pkey[x]);
-        if (c < 0) c = t->add_node(edge_ckey[x]);
+    for (int64_t x = 0; x < ne; ++x) {
+        int p = t->node_of((uint64_t)ep[x]), c = t->node_of((uint64_t)ec[x]);
+        if (p < 0) p = t->add_node((uint64_t)ep[x]);
+        if (c < 0) c = t->add_node((uint64_t)ec[x]);
         int e = t->edge_of(p, c);
         if (e < 0) e = t->add_edge(p, c);
+        double dr; memcpy(&dr, &er[x], 8);
         Edge& ed = t->edges[e];
-        ed.visits += edge_dv[x]; ed.reward += edge_dr[x];
-        ed.sync_visits += edge_dv[x]; ed.sync_reward += edge_dr[x];
+        ed.visits += ev[x]; ed.reward += dr;
+        ed.sync_visits += ev[x]; ed.sync_reward += dr;
     }
+    if (t->track_exhaustion) {
+        for (int64_t x = 0; x < nx; ++x) {
+            const int id = t->node_of((uint64_t)xk[x]);
+            if (id < 0 || t->nodes[id].exhausted) continue;    // (unknown: filtered out by max_depth)
+            t->mark_exhausted(id, false);
+        }
+        t->settle_exhausted();
+    }
+    if (buf[4] & 1) t->exhausted_all = true;
+    if (tree_exhausted) *tree_exhausted = t->exhausted_all ? 1 : 0;
     return CT_OK;
 }
 

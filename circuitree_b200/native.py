@@ -19,7 +19,7 @@ import numpy as np
 from . import _capi
 from .models import SimpleNetworkGrammar
 
-__all__ = ["NativeTree", "NativeExhaustionError"]
+__all__ = ["NativeTree", "NativeExhaustionError", "SearchPipeline"]
 
 _bound = False
 
@@ -51,13 +51,13 @@ def _lib():
         L.ct_tree_do_action.argtypes = [vp, u64, i32, ctypes.POINTER(u64)]
         L.ct_tree_key_to_handle.argtypes = [vp, u64, ctypes.POINTER(u64)]
         L.ct_tree_grow.argtypes = [vp]
-        L.ct_tree_collect_deltas.argtypes = [vp, ctypes.POINTER(i64), vp, vp, vp, ctypes.POINTER(i64), vp, vp, vp, vp]
-        L.ct_tree_merge_deltas.argtypes = [vp, i64, vp, vp, vp, i64, vp, vp, vp, vp]
+        L.ct_tree_pack_deltas.argtypes = [vp, i32, vp, i64, ctypes.POINTER(i64)]
+        L.ct_tree_merge_packed.argtypes = [vp, vp, i64, ctypes.POINTER(i32)]
         for name in ("ct_tree_create", "ct_tree_destroy", "ct_tree_set_rng", "ct_tree_get_rng", "ct_tree_set_log_table",
                      "ct_tree_rng_draw", "ct_tree_select", "ct_tree_backprop", "ct_tree_pending", "ct_tree_size",
                      "ct_tree_export", "ct_tree_key_to_string", "ct_tree_string_to_key", "ct_tree_actions",
-                     "ct_tree_do_action", "ct_tree_key_to_handle", "ct_tree_grow", "ct_tree_collect_deltas",
-                     "ct_tree_merge_deltas"):
+                     "ct_tree_do_action", "ct_tree_key_to_handle", "ct_tree_grow", "ct_tree_pack_deltas",
+                     "ct_tree_merge_packed"):
             getattr(L, name).restype = ctypes.c_int
         _bound = True
     return L
@@ -246,47 +246,16 @@ class NativeTree:
         virtual loss exactly as in the reference's parallel mode (circuitree.py:532-535) -- while
         earlier batches are still simulating, so their kernels overlap on the GPU.  Rewards are
         back-propagated in selection order.
-        """
-        import time
-        from collections import deque
 
-        inflight: deque = deque()
-        step = 0        # leaves selected
-        done = 0        # leaves back-propagated
-        if self.reward_fn is None:
-            self.reward_engine.share = max(1, int(pipeline_depth))     # batches in flight share the device
-
-        def retire():
-            nonlocal done
-            k, keys, paths, job = inflight.popleft()
-            t0 = time.perf_counter()
-            rewards = self._collect(job)
-            t1 = time.perf_counter()
-            self.backprop(rewards)
-            self.timing["reward_s"] += t1 - t0
-            self.timing["backprop_s"] += time.perf_counter() - t1
-            if callback is not None:
-                for x in range(k):
-                    callback(self, done + x, paths[x], self.key_to_string(int(keys[x])), float(rewards[x]))
-            done += k
-
-        while step < n_steps:
-            k = min(batch_size, n_steps - step)
-            t0 = time.perf_counter()
-            keys, handles = self.select(k)
-            t1 = time.perf_counter()
-            paths = self.pending_paths()[-k:] if callback is not None else None
-            job = self._submit(keys, handles)
-            self.timing["select_s"] += t1 - t0
-            self.timing["submit_s"] += time.perf_counter() - t1
-            inflight.append((k, keys, paths, job))
-            step += k
-            while len(inflight) >= max(1, pipeline_depth):
-                retire()
-        while inflight:
-            retire()
-        if self.reward_fn is None:
-            self.reward_engine.share = 1
+        Exhaustion (finite ``n_exhausted``) with leaves in flight follows the reference's greenlet
+        semantics (circuitree.py:377-420 under :786-893): flagging a node un-counts the edge totals
+        of that moment -- including the virtual visits of in-flight leaves -- from its parents, and a
+        reward that arrives later is still added along its whole path."""
+        pipe = SearchPipeline(self, batch_size, pipeline_depth, callback)
+        try:
+            pipe.advance(n_steps)
+        finally:
+            pipe.drain()
 
     def grow_tree(self) -> None:
         _check(_lib().ct_tree_grow(self._h))
@@ -326,20 +295,107 @@ class NativeTree:
         return g
 
     # -- multi-GPU merge --------------------------------------------------------------------------------------
-    def collect_deltas(self) -> dict:
-        nn, ne = ctypes.c_int64(0), ctypes.c_int64(0)
-        _check(_lib().ct_tree_collect_deltas(self._h, ctypes.byref(nn), None, None, None, ctypes.byref(ne), None, None, None, None))
-        d = {"node_key": np.zeros(nn.value, np.uint64), "node_dv": np.zeros(nn.value, np.int64), "node_dr": np.zeros(nn.value, np.float64),
-             "edge_pkey": np.zeros(ne.value, np.uint64), "edge_ckey": np.zeros(ne.value, np.uint64),
-             "edge_dv": np.zeros(ne.value, np.int64), "edge_dr": np.zeros(ne.value, np.float64)}
-        if nn.value or ne.value:
-            _check(_lib().ct_tree_collect_deltas(self._h, ctypes.byref(nn), d["node_key"].ctypes.data, d["node_dv"].ctypes.data,
-                                                 d["node_dr"].ctypes.data, ctypes.byref(ne), d["edge_pkey"].ctypes.data,
-                                                 d["edge_ckey"].ctypes.data, d["edge_dv"].ctypes.data, d["edge_dr"].ctypes.data))
+    PACK_HEADER = 5
+
+    def pack_deltas(self, out: Optional[np.ndarray] = None, max_depth: int = -1) -> np.ndarray:
+        """What this replica did since the previous call (sparse statistic increments + exhaustion
+        events) as one int64 buffer (``ct_tree_pack_deltas``).  ``out``: a caller-owned int64 array
+        (e.g. the numpy view of a pinned torch tensor) used when it is large enough."""
+        n = ctypes.c_int64(0)
+        _check(_lib().ct_tree_pack_deltas(self._h, int(max_depth), None, 0, ctypes.byref(n)))
+        if out is None or out.size < n.value:
+            out = np.empty(max(int(n.value), self.PACK_HEADER), dtype=np.int64)
+        _check(_lib().ct_tree_pack_deltas(self._h, int(max_depth), out.ctypes.data, out.size, ctypes.byref(n)))
+        return out[: n.value]
+
+    def merge_packed(self, buf: np.ndarray) -> bool:
+        """Add another replica's :meth:`pack_deltas` buffer; True when the whole tree is exhausted."""
+        buf = np.ascontiguousarray(buf, dtype=np.int64)
+        flag = ctypes.c_int32(0)
+        _check(_lib().ct_tree_merge_packed(self._h, buf.ctypes.data, buf.size, ctypes.byref(flag)))
+        return bool(flag.value)
+
+    @staticmethod
+    def unpack_deltas(buf: np.ndarray) -> dict:
+        """Readable view of a packed buffer (tests, diagnostics)."""
+        nn, ne, nx = int(buf[1]), int(buf[2]), int(buf[3])
+        o, out = NativeTree.PACK_HEADER, {"tree_exhausted": bool(buf[4] & 1)}
+        for name, n, dt in (("node_key", nn, np.uint64), ("node_dv", nn, np.int64), ("node_dr", nn, np.float64),
+                            ("edge_pkey", ne, np.uint64), ("edge_ckey", ne, np.uint64), ("edge_dv", ne, np.int64),
+                            ("edge_dr", ne, np.float64), ("exhausted", nx, np.uint64)):
+            out[name] = buf[o: o + n].view(dt)
+            o += n
+        return out
+
+    # dict-style aliases of the two calls above
+    def collect_deltas(self, max_depth: int = -1) -> dict:
+        buf = self.pack_deltas(max_depth=max_depth)
+        d = self.unpack_deltas(buf)
+        d["packed"] = buf
         return d
 
-    def merge_deltas(self, d: dict) -> None:
-        arrs = {k: np.ascontiguousarray(v) for k, v in d.items()}
-        _check(_lib().ct_tree_merge_deltas(self._h, len(arrs["node_key"]), arrs["node_key"].ctypes.data, arrs["node_dv"].ctypes.data,
-                                           arrs["node_dr"].ctypes.data, len(arrs["edge_pkey"]), arrs["edge_pkey"].ctypes.data,
-                                           arrs["edge_ckey"].ctypes.data, arrs["edge_dv"].ctypes.data, arrs["edge_dr"].ctypes.data))
+    def merge_deltas(self, d: dict) -> bool:
+        return self.merge_packed(d["packed"])
+
+
+class SearchPipeline:
+    """The select -> submit -> collect -> back-propagate loop of :meth:`NativeTree.search_mcts` as
+    an object, so that a caller (``RootParallelSearch``) can do other work -- a statistics merge --
+    between :meth:`advance` calls while reward batches stay in flight on the GPU."""
+
+    def __init__(self, tree: NativeTree, batch_size: int = 1, pipeline_depth: int = 1, callback: Optional[Callable] = None):
+        from collections import deque
+
+        self.tree = tree
+        self.batch_size = max(1, int(batch_size))
+        self.depth = max(1, int(pipeline_depth))
+        self.callback = callback
+        self.inflight = deque()
+        self.selected = 0      # leaves selected
+        self.done = 0          # leaves back-propagated
+        if tree.reward_fn is None:
+            tree.reward_engine.share = self.depth      # batches in flight share the device
+
+    def _retire(self) -> None:
+        import time
+
+        tree = self.tree
+        k, keys, paths, job = self.inflight.popleft()
+        t0 = time.perf_counter()
+        rewards = tree._collect(job)
+        t1 = time.perf_counter()
+        tree.backprop(rewards)
+        tree.timing["reward_s"] += t1 - t0
+        tree.timing["backprop_s"] += time.perf_counter() - t1
+        if self.callback is not None:
+            for x in range(k):
+                self.callback(tree, self.done + x, paths[x], tree.key_to_string(int(keys[x])), float(rewards[x]))
+        self.done += k
+
+    def advance(self, n_steps: int) -> None:
+        """Select and submit ``n_steps`` more leaves; retire batches only as the depth requires."""
+        import time
+
+        tree = self.tree
+        left = int(n_steps)
+        while left > 0:
+            k = min(self.batch_size, left)
+            t0 = time.perf_counter()
+            keys, handles = tree.select(k)
+            t1 = time.perf_counter()
+            paths = tree.pending_paths()[-k:] if self.callback is not None else None
+            job = tree._submit(keys, handles)
+            tree.timing["select_s"] += t1 - t0
+            tree.timing["submit_s"] += time.perf_counter() - t1
+            self.inflight.append((k, keys, paths, job))
+            self.selected += k
+            left -= k
+            while len(self.inflight) >= self.depth:
+                self._retire()
+
+    def drain(self) -> None:
+        """Wait for and back-propagate every batch still in flight."""
+        while self.inflight:
+            self._retire()
+        if self.tree.reward_fn is None:
+            self.tree.reward_engine.share = 1

@@ -182,12 +182,15 @@ int ct_tree_actions(ct_tree *t, uint64_t key, int32_t *ids, int32_t cap, int32_t
 int ct_tree_do_action(ct_tree *t, uint64_t key, int32_t action, uint64_t *out);
 int ct_tree_key_to_handle(ct_tree *t, uint64_t key, uint64_t *handle);
 int ct_tree_grow(ct_tree *t);
-/* Root-parallel merge across GPUs: sparse (state key, d visits, d reward) records. */
-int ct_tree_collect_deltas(ct_tree *t, int64_t *n_node_recs, uint64_t *node_key, int64_t *node_dv, double *node_dr,
-                           int64_t *n_edge_recs, uint64_t *edge_pkey, uint64_t *edge_ckey, int64_t *edge_dv, double *edge_dr);
-int ct_tree_merge_deltas(ct_tree *t, int64_t n_node_recs, const uint64_t *node_key, const int64_t *node_dv,
-                         const double *node_dr, int64_t n_edge_recs, const uint64_t *edge_pkey, const uint64_t *edge_ckey,
-                         const int64_t *edge_dv, const double *edge_dr);
+/* Root-parallel merge across GPUs (one tree per GPU, periodic exchange of statistics; the reference's
+ * only parallel search shares one graph between greenlets, circuitree.py:786-893).  pack writes what
+ * this replica did since the previous pack -- sparse (state key, d visits, d reward) records for
+ * nodes and edges plus the keys of nodes it flagged exhausted (circuitree.py:386-420) -- into one
+ * buffer of 64-bit words (layout: csrc/native_tree.cpp); with buf == NULL or cap too small it only
+ * reports the size needed.  max_depth >= 0 limits the exchange to states with at most that many
+ * interactions.  merge adds another replica's buffer and replays its exhaustion events. */
+int ct_tree_pack_deltas(ct_tree *t, int32_t max_depth, int64_t *buf, int64_t cap, int64_t *n_words);
+int ct_tree_merge_packed(ct_tree *t, const int64_t *buf, int64_t n_words, int32_t *tree_exhausted);
 
 #ifdef __cplusplus
 }

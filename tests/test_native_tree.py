@@ -209,6 +209,68 @@ def test_delta_merge_equals_single_tree_sums():
     assert len(digs) <= 3
 
 
+def test_delta_merge_with_finite_n_exhausted_keeps_replicas_consistent():
+    """Four replicas on ABC::, n_exhausted=4, merging every 128 steps: exhaustion travels as an event
+    (the un-counting is replayed once per replica, never exchanged as an increment), so visit counts
+    stay non-negative, the replicas agree node for node, and the search ends with the reference's
+    ExhaustionError on every replica instead of a dead end."""
+    from circuitree_b200.native import NativeExhaustionError
+
+    reps = [NativeTree(SimpleNetworkGrammar(list("ABC"), AI, max_interactions=3), "ABC::", seed=10 + s, n_exhausted=4,
+                       reward_fn=crc_rewards) for s in range(4)]
+    exhausted = [False] * 4
+    rounds = 0
+    while not all(exhausted) and rounds < 2000:
+        for i, r in enumerate(reps):
+            if exhausted[i]:
+                continue
+            try:
+                r.search_mcts(128, batch_size=16)
+            except NativeExhaustionError:
+                exhausted[i] = True
+        bufs = [r.pack_deltas().copy() for r in reps]
+        for i, r in enumerate(reps):
+            for j, b in enumerate(bufs):
+                if i != j and r.merge_packed(b):
+                    exhausted[i] = True
+        rounds += 1
+        exports = [r.export() for r in reps]
+        assert all((e["node_visits"] >= 0).all() and (e["edge_visits"] >= 0).all() for e in exports), rounds
+        ref = {int(k): (int(v), bool(x)) for k, v, x in zip(exports[0]["node_keys"], exports[0]["node_visits"], exports[0]["node_exhausted"])}
+        for e in exports[1:]:
+            other = {int(k): (int(v), bool(x)) for k, v, x in zip(e["node_keys"], e["node_visits"], e["node_exhausted"])}
+            assert other == ref, rounds
+    assert all(exhausted) and rounds > 1
+    g = reps[0].to_networkx()
+    assert g.nodes["ABC::"].get("is_exhausted")
+    assert all(d.get("is_exhausted") for n, d in g.nodes(data=True) if n.startswith("*"))
+    for r in reps:      # an exhausted tree selects nothing more
+        with pytest.raises(NativeExhaustionError):
+            r.search_mcts(1)
+
+
+def test_depth_limited_exchange():
+    a, twin, b = native(3, "ABC::", 1), native(3, "ABC::", 1), native(3, "ABC::", 2)
+    a.search_mcts(300, batch_size=8)
+    twin.search_mcts(300, batch_size=8)
+    full = twin.collect_deltas()
+    d = a.collect_deltas(max_depth=2)
+    assert 0 < len(d["node_key"]) < len(full["node_key"])
+    b.merge_deltas(d)
+    gb = b.to_networkx()
+    assert gb.nodes["ABC::"]["visits"] == 300
+
+    def depth(name):
+        body = name.split("::")[1]
+        return (len(body.split("_")) if body else 0) + name.startswith("*")
+
+    assert max(depth(n) for n in gb.nodes) == 2
+    # what was held back is still pending: a later unrestricted exchange delivers the rest exactly once
+    b.merge_deltas(a.collect_deltas())
+    ga, gb = a.to_networkx(), b.to_networkx()
+    assert {n: ga.nodes[n]["visits"] for n in ga.nodes} == {n: gb.nodes[n]["visits"] for n in gb.nodes}
+
+
 def test_unsupported_configurations_are_refused():
     from circuitree_b200 import _capi
 
