@@ -406,7 +406,15 @@ class CircuiTree(MotifMixin, ABC):
 
         ``pipeline_depth > 1`` keeps that many reward batches in flight (:meth:`submit_rewards` /
         :meth:`collect_rewards`): the next batch is selected, with the visits of every in-flight leaf
-        already counted, while earlier batches are still being simulated."""
+        already counted, while earlier batches are still being simulated.
+
+        Finite ``n_exhausted`` with leaves in flight follows what the reference's greenlets do when
+        they all block in ``get_reward`` (circuitree.py:377-420 under :786-893): flagging a node
+        un-counts the edge totals of that moment -- virtual visits of in-flight leaves included --
+        from its parents, and a reward that arrives later is still added along its whole path.  When
+        the tree is exhausted (``ExhaustionError``) the complete batches in flight are finished first;
+        the leaves of the batch being selected keep their visits and never get rewards.  Pinned by
+        tests/golden/batched_vectors.json.gz (reference methods driven in this schedule)."""
         if batch_size < 1:
             raise ValueError("batch_size must be at least 1.")
         if pipeline_depth < 1:
@@ -428,23 +436,25 @@ class CircuiTree(MotifMixin, ABC):
                     callback(self, step, path, sim, reward)
                 step += 1
 
-        while selected < n_steps:
-            k = min(batch_size, n_steps - selected)
-            paths, sims = [], []
-            for _ in range(k):
-                path = self.select_and_expand()
-                sims.append(self.get_random_terminal_descendant(path[-1]))
-                self.backpropagate_visit(path)
-                paths.append(path)
-            selected += k
-            if pipeline_depth == 1:
-                inflight.append((paths, sims, list(self.get_rewards(sims, **run_kwargs))))
-            else:
-                inflight.append((paths, sims, self.submit_rewards(sims, **run_kwargs)))
-            while len(inflight) >= pipeline_depth:
+        try:
+            while selected < n_steps:
+                k = min(batch_size, n_steps - selected)
+                paths, sims = [], []
+                for _ in range(k):
+                    path = self.select_and_expand()
+                    sims.append(self.get_random_terminal_descendant(path[-1]))
+                    self.backpropagate_visit(path)
+                    paths.append(path)
+                selected += k
+                if pipeline_depth == 1:
+                    inflight.append((paths, sims, list(self.get_rewards(sims, **run_kwargs))))
+                else:
+                    inflight.append((paths, sims, self.submit_rewards(sims, **run_kwargs)))
+                while len(inflight) >= pipeline_depth:
+                    retire()
+        finally:
+            while inflight:
                 retire()
-        while inflight:
-            retire()
 
     def search_mcts_parallel(self, n_steps: int, n_threads: int, callback: Optional[Callable] = None,
                              callback_every: int = 1, callback_before_start: bool = True,

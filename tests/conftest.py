@@ -29,3 +29,10 @@ def ref_vectors():
 @pytest.fixture(scope="session")
 def simple3_space():
     return _load("simple3_space.json.gz")
+
+
+@pytest.fixture(scope="session")
+def batched_vectors():
+    """Reference methods driven in the batched (greenlets-blocked-in-get_reward) schedule with finite
+    n_exhausted (tests/golden/make_golden.py section 9)."""
+    return _load("batched_vectors.json.gz")

@@ -217,6 +217,60 @@ def main():
                     "reward": "crc32(state) % 1000 / 1000"}
     dump("reference_vectors", out, compress=True)
 
+    # ---- 9. exhaustion with leaves in flight (separate fixture: batched_vectors.json.gz) -----------
+    # The reference's parallel mode (circuitree.py:786-893) needs gevent, which is not installed; what
+    # it does is interleave greenlets at get_reward.  The schedule below is the interleaving that
+    # results when `batch` greenlets all block in get_reward together and `depth` such groups are
+    # outstanding: the reference's OWN select_and_expand / rollout / backpropagate_visit run for a whole
+    # group (virtual loss, :529-533) before any of its rewards is back-propagated (:534-535), in
+    # selection order.  On ExhaustionError the complete groups still in flight are finished; the
+    # partially selected group keeps its visits and never gets rewards (greenlets that died).
+    def run_batched(grammar, root, n, seed, n_exhausted, batch, depth):
+        tr = CrcTree(grammar=grammar, root=root, seed=seed, n_exhausted=n_exhausted)
+        inflight, digests, err, selected = [], [], None, 0
+
+        def retire():
+            for path, sim in inflight.pop(0):
+                reward = tr.get_reward(sim)
+                tr.backpropagate_reward(path, reward)
+                digests.append(step_digest(path, sim, reward))
+
+        try:
+            while selected < n:
+                k = min(batch, n - selected)
+                group = []
+                for _ in range(k):
+                    path = tr.select_and_expand()
+                    sim = tr.get_random_terminal_descendant(path[-1])
+                    tr.backpropagate_visit(path)
+                    group.append((path, sim))
+                    selected += 1
+                inflight.append(group)
+                while len(inflight) >= depth:
+                    retire()
+        except ExhaustionError:
+            err = "ExhaustionError"
+        while inflight:
+            retire()
+        return {"n_selected": selected, "n_done": len(digests), "digests": digests, "error": err,
+                "n_nodes": tr.graph.number_of_nodes(), "n_edges": tr.graph.number_of_edges(),
+                "graph_digest": graph_digest(tr.graph),
+                "n_flagged": sum(bool(a.get("is_exhausted", False)) for _, a in tr.graph.nodes(data=True)),
+                "min_node_visits": min(a["visits"] for _, a in tr.graph.nodes(data=True)),
+                "root_visits": tr.graph.nodes[root]["visits"], "root_reward": tr.graph.nodes[root]["reward"]}
+
+    g3m3 = SimpleNetworkGrammar(components=["A", "B", "C"], interactions=["activates", "inhibits"], max_interactions=3)
+    bat = {
+        "b8_d1_exh3": dict(args=["g3", "ABC::", 4000, 5, 3, 8, 1], res=run_batched(g3, "ABC::", 4000, 5, 3, 8, 1)),
+        "b16_d3_exh4": dict(args=["g3", "ABC::", 6000, 6, 4, 16, 3], res=run_batched(g3, "ABC::", 6000, 6, 4, 16, 3)),
+        "b8_d2_exh2_to_the_end": dict(args=["g3m3", "ABC::", 100000, 7, 2, 8, 2], res=run_batched(g3m3, "ABC::", 100000, 7, 2, 8, 2)),
+        "b5_d2_two_components": dict(args=["g2", "AB::", 100000, 3, 3, 5, 2], res=run_batched(g2, "AB::", 100000, 3, 3, 5, 2)),
+        "b1_d1_is_sequential": dict(args=["g3", "ABC::", 2500, 5, 2, 1, 1], res=run_batched(g3, "ABC::", 2500, 5, 2, 1, 1)),
+    }
+    assert bat["b1_d1_is_sequential"]["res"]["graph_digest"] == out["mcts3_exhaust"]["graph_digest"]
+    bat["_meta"] = dict(out["_meta"], schedule="groups of `batch` leaves selected under virtual loss, `depth` groups in flight")
+    dump("batched_vectors", bat, compress=True)
+
 
 if __name__ == "__main__":
     main()

@@ -122,6 +122,28 @@ class CrcTree(CircuiTree):
         return crc_reward(state)
 
 
+@pytest.mark.parametrize("key", ["b8_d1_exh3", "b16_d3_exh4", "b8_d2_exh2_to_the_end", "b5_d2_two_components",
+                                 "b1_d1_is_sequential"])
+def test_native_exhaustion_with_leaves_in_flight(batched_vectors, key):
+    """Row f3 on the native tree: same schedule, same bits as the reference's own methods."""
+    gname, root, steps, seed, n_exh, batch, depth = batched_vectors[key]["args"]
+    gold = batched_vectors[key]["res"]
+    g = {"g3": grammar(3), "g2": grammar(2), "g3m3": SimpleNetworkGrammar(list("ABC"), AI, max_interactions=3)}[gname]
+    t = NativeTree(g, root, seed=seed, n_exhausted=n_exh, reward_fn=crc_rewards)
+    digests, err = [], None
+    try:
+        t.search_mcts(steps, batch_size=batch, pipeline_depth=depth,
+                      callback=lambda tr, i, p, s, r: digests.append(step_digest(p, s, r)))
+    except NativeExhaustionError:
+        err = "ExhaustionError"
+    assert err == gold["error"]
+    assert digests == gold["digests"]
+    nx_g = t.to_networkx()
+    assert (nx_g.number_of_nodes(), nx_g.number_of_edges()) == (gold["n_nodes"], gold["n_edges"])
+    assert graph_digest(nx_g) == gold["graph_digest"]
+    assert nx_g.nodes[root]["visits"] == gold["root_visits"] and nx_g.nodes[root]["reward"] == gold["root_reward"]
+
+
 @pytest.mark.parametrize("batch", [7, 64])
 def test_native_batched_equals_python_batched(batch):
     """Virtual-loss batching: same leaves, same statistics, same RNG state as the Python scheduler."""

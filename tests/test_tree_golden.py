@@ -85,6 +85,32 @@ def test_batched_with_batch_one_equals_sequential(ref_vectors):
     assert graph_digest(tree.graph) == gold["graph_digest"]
 
 
+BATCHED = ["b8_d1_exh3", "b16_d3_exh4", "b8_d2_exh2_to_the_end", "b5_d2_two_components", "b1_d1_is_sequential"]
+
+
+def batched_grammar(name):
+    return {"g3": grammar(3), "g2": grammar(2), "g3m3": SimpleNetworkGrammar(list("ABC"), AI, max_interactions=3)}[name]
+
+
+@pytest.mark.parametrize("key", BATCHED)
+def test_exhaustion_with_leaves_in_flight_matches_reference_schedule(batched_vectors, key):
+    """finite n_exhausted under batching / pipelining."""
+    gname, root, steps, seed, n_exh, batch, depth = batched_vectors[key]["args"]
+    gold = batched_vectors[key]["res"]
+    tree = CrcTree(grammar=batched_grammar(gname), root=root, seed=seed, n_exhausted=n_exh)
+    digests, err = [], None
+    try:
+        tree.search_mcts_batched(steps, batch, pipeline_depth=depth, callback_before_start=False,
+                                 callback=lambda t, i, p, s, r: digests.append(step_digest(p, s, r)))
+    except ExhaustionError:
+        err = "ExhaustionError"
+    assert err == gold["error"]
+    assert digests == gold["digests"]
+    assert (tree.graph.number_of_nodes(), tree.graph.number_of_edges()) == (gold["n_nodes"], gold["n_edges"])
+    assert graph_digest(tree.graph) == gold["graph_digest"]
+    assert tree.graph.nodes[root]["visits"] == gold["root_visits"] and tree.graph.nodes[root]["reward"] == gold["root_reward"]
+
+
 def test_batched_virtual_loss_conserves_counts():
     tree = CrcTree(grammar=grammar(3), root="ABC::", seed=3, n_exhausted=np.inf)
     tree.search_mcts_batched(1000, 64)
