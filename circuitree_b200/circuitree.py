@@ -498,7 +498,7 @@ class CircuiTree(MotifMixin, ABC):
         if attrs_copy is None:
             keys = set(self.__dict__) - blocked
         else:
-            keys = set(attrs_copy)
+            keys = set(attrs_copy) & set(self.__dict__)
             bad = keys & blocked
             if bad:
                 raise ValueError(f"Attempting to save non-serializable attributes: {', '.join(bad)}.")

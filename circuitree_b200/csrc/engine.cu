@@ -42,6 +42,34 @@ struct KernelInfo {
     size_t smem = 0;
 };
 
+// Stream-ordered scratch of one call: everything handed out is released (cudaFreeAsync on the same
+// stream, i.e. after the work enqueued so far) when the object goes out of scope -- on every error
+// return as well as on success.  keep() takes a buffer out (it then belongs to a Ticket).
+struct StreamScratch {
+    cudaStream_t stream;
+    std::vector<void*> ptrs;
+    explicit StreamScratch(cudaStream_t s) : stream(s) {}
+    StreamScratch(const StreamScratch&) = delete;
+    StreamScratch& operator=(const StreamScratch&) = delete;
+    template <typename T>
+    cudaError_t alloc(T** out, size_t bytes)
+    {
+        void* p = nullptr;
+        cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 1, stream);
+        if (e == cudaSuccess) ptrs.push_back(p);
+        *out = static_cast<T*>(p);
+        return e;
+    }
+    void keep(void* p)
+    {
+        for (auto& q : ptrs) if (q == p) q = nullptr;
+    }
+    ~StreamScratch()
+    {
+        for (void* p : ptrs) if (p) cudaFreeAsync(p, stream);
+    }
+};
+
 // Process-wide, append-only table of dimer topologies (SPEC.md section 9); a k = 3 handle is
 // kDimerTag | n_tf << 56 | index into this table.
 constexpr uint64_t kDimerTag = 1ull << 63;
@@ -68,6 +96,7 @@ struct Ticket {                      // one asynchronous reward batch in flight
     double* d_mean = nullptr;
     uint64_t* d_jev = nullptr;
 };
+void release_ticket(Ticket& t);
 }  // namespace
 
 struct ct_engine {
@@ -197,10 +226,8 @@ int ct_engine_destroy(ct_engine* eng)
 {
     if (!eng) return CT_OK;
     cudaSetDevice(eng->device);
-    for (auto& kv : eng->tickets) {
-        cudaStreamSynchronize(kv.second.stream);
-        cudaStreamDestroy(kv.second.stream);
-    }
+    for (auto& kv : eng->tickets) release_ticket(kv.second);     // batches nobody waited for
+    if (eng->d_warp_iters) cudaFree(eng->d_warp_iters);
     if (eng->stream) cudaStreamDestroy(eng->stream);
     delete eng;
     return CT_OK;
@@ -367,10 +394,11 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
     if (d_series && series_stride < (int)max_nsp * (cfg->nt / cfg->decim))
         return fail(CT_ERR_INVALID, "series_stride %d too small", series_stride);
 
+    StreamScratch scratch(stream);      // released in stream order when this call returns, whatever the path
     ct::Job* d_jobs = nullptr;
     uint32_t* d_counter = nullptr;
-    CT_CUDA(cudaMallocAsync((void**)&d_jobs, sizeof(ct::Job) * jobs.size(), stream));
-    CT_CUDA(cudaMallocAsync((void**)&d_counter, sizeof(uint32_t), stream));
+    CT_CUDA(scratch.alloc(&d_jobs, sizeof(ct::Job) * jobs.size()));
+    CT_CUDA(scratch.alloc(&d_counter, sizeof(uint32_t)));
     CT_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(ct::Job) * jobs.size(), cudaMemcpyHostToDevice, stream));
     CT_CUDA(cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), stream));
 
@@ -427,12 +455,14 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
     float* d_job_cost = nullptr;
     void* d_tmp = nullptr;
     if (cfg->lpt && total > 1) {
-        CT_CUDA(cudaMallocAsync((void**)&d_keys, sizeof(unsigned long long) * total, stream));
-        CT_CUDA(cudaMallocAsync((void**)&d_keys_out, sizeof(unsigned long long) * total, stream));
-        CT_CUDA(cudaMallocAsync((void**)&d_slots, sizeof(uint32_t) * total, stream));
-        CT_CUDA(cudaMallocAsync((void**)&d_order, sizeof(uint32_t) * total, stream));
+        if (total > 0x7fffffffull)
+            return fail(CT_ERR_INVALID, "longest-first ordering (cfg.lpt) takes at most 2^31-1 trajectories per launch");
+        CT_CUDA(scratch.alloc(&d_keys, sizeof(unsigned long long) * total));
+        CT_CUDA(scratch.alloc(&d_keys_out, sizeof(unsigned long long) * total));
+        CT_CUDA(scratch.alloc(&d_slots, sizeof(uint32_t) * total));
+        CT_CUDA(scratch.alloc(&d_order, sizeof(uint32_t) * total));
         if (job_cost) {
-            CT_CUDA(cudaMallocAsync((void**)&d_job_cost, sizeof(float) * n_jobs, stream));
+            CT_CUDA(scratch.alloc(&d_job_cost, sizeof(float) * n_jobs));
             CT_CUDA(cudaMemcpyAsync(d_job_cost, job_cost, sizeof(float) * n_jobs, cudaMemcpyHostToDevice, stream));
         }
         ct::cost_key_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(A, d_job_cost, mixed ? 0 : 1, d_keys, d_slots);
@@ -442,7 +472,7 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
         size_t tmp_bytes = 0;
         CT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys_out, d_slots, d_order, (int)total, 0,
                                                 end_bit, stream));
-        CT_CUDA(cudaMallocAsync(&d_tmp, tmp_bytes ? tmp_bytes : 1, stream));
+        CT_CUDA(scratch.alloc(&d_tmp, tmp_bytes));
         CT_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys_out, d_slots, d_order, (int)total, 0,
                                                 end_bit, stream));
         eng->launches += 2;
@@ -453,7 +483,7 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
         void* d_progs = nullptr;
         const void* h_progs = mixed ? (const void*)lane_progs.data() : (const void*)progs.data();
         const size_t prog_bytes = mixed ? sizeof(ct::DimerLaneProg) * lane_progs.size() : sizeof(ct::DimerProg) * progs.size();
-        CT_CUDA(cudaMallocAsync(&d_progs, prog_bytes, stream));
+        CT_CUDA(scratch.alloc(&d_progs, prog_bytes));
         CT_CUDA(cudaMemcpyAsync(d_progs, h_progs, prog_bytes, cudaMemcpyHostToDevice, stream));
         const size_t smem = (mixed ? shape.warp_bytes() : lay.warp_bytes()) * (ct::kDimThreads / 32);
         const size_t rec_lane = mixed ? shape.rec_lane_bytes() : lay.rec_lane_bytes();
@@ -467,23 +497,14 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
             cap = (uint64_t)cfg->grid_limit * (ct::kThreads / ct::kDimThreads);   // grid_limit counts 128-thread CTAs
         const unsigned dgrid = (unsigned)(want < cap ? want : cap);
         uint8_t* d_records = nullptr;      // per-lane record scratch (see ssa_dimers.cuh)
-        CT_CUDA(cudaMallocAsync((void**)&d_records, (size_t)dgrid * ct::kDimThreads * rec_lane, stream));
+        CT_CUDA(scratch.alloc(&d_records, (size_t)dgrid * ct::kDimThreads * rec_lane));
         if (mixed)
             ct::ssa_dimers_mixed_kernel<<<dgrid, ct::kDimThreads, smem, stream>>>(A, (const ct::DimerLaneProg*)d_progs, shape, d_records);
         else
             ct::ssa_dimers_kernel<<<dgrid, ct::kDimThreads, smem, stream>>>(A, (const ct::DimerProg*)d_progs, lay, d_records);
         CT_CUDA(cudaGetLastError());
         eng->launches += 1;
-        // (pageable host memory: the copy above has been staged when cudaMemcpyAsync returns)
-        CT_CUDA(cudaFreeAsync(d_records, stream));
-        CT_CUDA(cudaFreeAsync(d_progs, stream));
-        CT_CUDA(cudaFreeAsync(d_jobs, stream));
-        CT_CUDA(cudaFreeAsync(d_counter, stream));
-        if (d_keys) {
-            cudaFreeAsync(d_keys, stream); cudaFreeAsync(d_keys_out, stream); cudaFreeAsync(d_slots, stream);
-            cudaFreeAsync(d_order, stream); cudaFreeAsync(d_tmp, stream);
-            if (d_job_cost) cudaFreeAsync(d_job_cost, stream);
-        }
+        // (pageable host memory: the copies above have been staged when cudaMemcpyAsync returns)
         return CT_OK;
     }
     const int mm = max_nsp <= 3 ? 3 : (int)max_nsp;
@@ -516,13 +537,6 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
 #undef CT_LAUNCH
     CT_CUDA(cudaGetLastError());
     eng->launches += 1;
-    CT_CUDA(cudaFreeAsync(d_jobs, stream));
-    CT_CUDA(cudaFreeAsync(d_counter, stream));
-    if (d_keys) {
-        cudaFreeAsync(d_keys, stream); cudaFreeAsync(d_keys_out, stream); cudaFreeAsync(d_slots, stream);
-        cudaFreeAsync(d_order, stream); cudaFreeAsync(d_tmp, stream);
-        if (d_job_cost) cudaFreeAsync(d_job_cost, stream);
-    }
     return CT_OK;
 }
 
@@ -538,8 +552,9 @@ int ct_reduce_jobs(ct_engine* eng, const uint32_t* n_traj, int32_t n_jobs, void*
     uint64_t total = 0;
     for (int j = 0; j < n_jobs; ++j) { off[j] = (uint32_t)total; total += n_traj[j]; }
     off[n_jobs] = (uint32_t)total;
+    StreamScratch scratch(stream);
     uint32_t* d_off = nullptr;
-    CT_CUDA(cudaMallocAsync((void**)&d_off, sizeof(uint32_t) * off.size(), stream));
+    CT_CUDA(scratch.alloc(&d_off, sizeof(uint32_t) * off.size()));
     CT_CUDA(cudaMemcpyAsync(d_off, off.data(), sizeof(uint32_t) * off.size(), cudaMemcpyHostToDevice, stream));
     const int warps_per_block = 8;
     const unsigned grid = (unsigned)((n_jobs + warps_per_block - 1) / warps_per_block);
@@ -547,7 +562,6 @@ int ct_reduce_jobs(ct_engine* eng, const uint32_t* n_traj, int32_t n_jobs, void*
                                                                       (unsigned long long*)d_job_events);
     CT_CUDA(cudaGetLastError());
     eng->launches += 1;
-    CT_CUDA(cudaFreeAsync(d_off, stream));
     return CT_OK;
 }
 
@@ -571,36 +585,75 @@ int ct_rewards_host(ct_engine* eng, const uint64_t* handles, const uint32_t* n_t
     uint32_t* d_events = nullptr;
     double* d_mean = nullptr;
     uint64_t* d_jev = nullptr;
-    CT_CUDA(cudaMallocAsync((void**)&d_reward, sizeof(float) * total, s));
-    CT_CUDA(cudaMallocAsync((void**)&d_lag, sizeof(int32_t) * total, s));
-    CT_CUDA(cudaMallocAsync((void**)&d_events, sizeof(uint32_t) * total, s));
-    CT_CUDA(cudaMallocAsync((void**)&d_mean, sizeof(double) * n_jobs, s));
-    CT_CUDA(cudaMallocAsync((void**)&d_jev, sizeof(uint64_t) * n_jobs, s));
-    if (h_params) {
-        const size_t np = (size_t)params_per_trajectory(handles, n_jobs);
-        CT_CUDA(cudaMallocAsync((void**)&d_params, sizeof(float) * total * np, s));
-        CT_CUDA(cudaMemcpyAsync(d_params, h_params, sizeof(float) * total * np, cudaMemcpyHostToDevice, s));
-    }
-    int rc = ct_launch_rewards(eng, handles, n_traj, traj_base, job_cost, n_jobs, cfg, seed, s, d_params, d_reward,
+    int rc;
+    {
+        StreamScratch scratch(s);       // freed in stream order at the end of this block, on every path
+        CT_CUDA(scratch.alloc(&d_reward, sizeof(float) * total));
+        CT_CUDA(scratch.alloc(&d_lag, sizeof(int32_t) * total));
+        CT_CUDA(scratch.alloc(&d_events, sizeof(uint32_t) * total));
+        CT_CUDA(scratch.alloc(&d_mean, sizeof(double) * n_jobs));
+        CT_CUDA(scratch.alloc(&d_jev, sizeof(uint64_t) * n_jobs));
+        if (h_params) {
+            const size_t np = (size_t)params_per_trajectory(handles, n_jobs);
+            CT_CUDA(scratch.alloc(&d_params, sizeof(float) * total * np));
+            CT_CUDA(cudaMemcpyAsync(d_params, h_params, sizeof(float) * total * np, cudaMemcpyHostToDevice, s));
+        }
+        rc = ct_launch_rewards(eng, handles, n_traj, traj_base, job_cost, n_jobs, cfg, seed, s, d_params, d_reward,
                                d_lag, d_events, nullptr, 0);
-    if (rc == CT_OK) rc = ct_reduce_jobs(eng, n_traj, n_jobs, s, d_reward, d_events, d_mean, d_jev);
-    if (rc == CT_OK) {
-        if (h_job_mean) CT_CUDA(cudaMemcpyAsync(h_job_mean, d_mean, sizeof(double) * n_jobs, cudaMemcpyDeviceToHost, s));
-        if (h_job_events) CT_CUDA(cudaMemcpyAsync(h_job_events, d_jev, sizeof(uint64_t) * n_jobs, cudaMemcpyDeviceToHost, s));
-        if (h_reward) CT_CUDA(cudaMemcpyAsync(h_reward, d_reward, sizeof(float) * total, cudaMemcpyDeviceToHost, s));
-        if (h_lag) CT_CUDA(cudaMemcpyAsync(h_lag, d_lag, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, s));
+        if (rc == CT_OK) rc = ct_reduce_jobs(eng, n_traj, n_jobs, s, d_reward, d_events, d_mean, d_jev);
+        if (rc == CT_OK) {
+            if (h_job_mean) CT_CUDA(cudaMemcpyAsync(h_job_mean, d_mean, sizeof(double) * n_jobs, cudaMemcpyDeviceToHost, s));
+            if (h_job_events) CT_CUDA(cudaMemcpyAsync(h_job_events, d_jev, sizeof(uint64_t) * n_jobs, cudaMemcpyDeviceToHost, s));
+            if (h_reward) CT_CUDA(cudaMemcpyAsync(h_reward, d_reward, sizeof(float) * total, cudaMemcpyDeviceToHost, s));
+            if (h_lag) CT_CUDA(cudaMemcpyAsync(h_lag, d_lag, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, s));
+        }
     }
-    cudaFreeAsync(d_reward, s);
-    cudaFreeAsync(d_lag, s);
-    cudaFreeAsync(d_events, s);
-    cudaFreeAsync(d_mean, s);
-    cudaFreeAsync(d_jev, s);
-    if (d_params) cudaFreeAsync(d_params, s);
-    cudaError_t e = cudaStreamSynchronize(s);
+    cudaError_t e = cudaStreamSynchronize(s);      // (also on failure: the caller's host buffers must not be in use afterwards)
     if (rc != CT_OK) return rc;
     if (e != cudaSuccess) return fail(CT_ERR_CUDA, "kernel execution failed: %s", cudaGetErrorString(e));
     return CT_OK;
 }
+
+}  // extern "C"
+
+namespace {
+// Body of ct_rewards_submit after the stream exists: allocate, copy, launch, reduce.  On success the
+// result buffers leave the scratch guard and belong to the ticket; on any failure the guard frees them.
+int submit_on_stream(ct_engine* eng, Ticket& t, const uint64_t* handles, const uint32_t* n_traj, const uint64_t* traj_base,
+                     const float* job_cost, int32_t n_jobs, const ct_sim_config* cfg, uint64_t seed, const float* h_params)
+{
+    cudaStream_t s = t.stream;
+    StreamScratch scratch(s);
+    CT_CUDA(scratch.alloc(&t.d_reward, sizeof(float) * t.total));
+    CT_CUDA(scratch.alloc(&t.d_lag, sizeof(int32_t) * t.total));
+    CT_CUDA(scratch.alloc(&t.d_events, sizeof(uint32_t) * t.total));
+    CT_CUDA(scratch.alloc(&t.d_mean, sizeof(double) * n_jobs));
+    CT_CUDA(scratch.alloc(&t.d_jev, sizeof(uint64_t) * n_jobs));
+    if (h_params) {
+        const size_t np = (size_t)params_per_trajectory(handles, n_jobs);
+        CT_CUDA(scratch.alloc(&t.d_params, sizeof(float) * t.total * np));
+        CT_CUDA(cudaMemcpyAsync(t.d_params, h_params, sizeof(float) * t.total * np, cudaMemcpyHostToDevice, s));
+    }
+    int rc = ct_launch_rewards(eng, handles, n_traj, traj_base, job_cost, n_jobs, cfg, seed, s, t.d_params, t.d_reward,
+                               t.d_lag, t.d_events, nullptr, 0);
+    if (rc == CT_OK) rc = ct_reduce_jobs(eng, n_traj, n_jobs, s, t.d_reward, t.d_events, t.d_mean, t.d_jev);
+    if (rc != CT_OK) return rc;
+    for (void* p : {(void*)t.d_reward, (void*)t.d_lag, (void*)t.d_events, (void*)t.d_mean, (void*)t.d_jev, (void*)t.d_params})
+        if (p) scratch.keep(p);
+    return CT_OK;
+}
+
+void release_ticket(Ticket& t)
+{
+    cudaStream_t s = t.stream;
+    for (void* p : {(void*)t.d_reward, (void*)t.d_lag, (void*)t.d_events, (void*)t.d_mean, (void*)t.d_jev, (void*)t.d_params})
+        if (p) cudaFreeAsync(p, s);
+    cudaStreamSynchronize(s);
+    cudaStreamDestroy(s);
+}
+}  // namespace
+
+extern "C" {
 
 // Asynchronous pair: submit enqueues the batch on a stream of its own and returns at once, so
 // the kernels of consecutive batches overlap (the tail of one launch -- a few long trajectories --
@@ -618,20 +671,9 @@ int ct_rewards_submit(ct_engine* eng, const uint64_t* handles, const uint32_t* n
     if (t.total == 0) return fail(CT_ERR_INVALID, "empty batch");
     CT_CUDA(cudaStreamCreateWithFlags(&t.stream, cudaStreamNonBlocking));
     cudaStream_t s = t.stream;
-    CT_CUDA(cudaMallocAsync((void**)&t.d_reward, sizeof(float) * t.total, s));
-    CT_CUDA(cudaMallocAsync((void**)&t.d_lag, sizeof(int32_t) * t.total, s));
-    CT_CUDA(cudaMallocAsync((void**)&t.d_events, sizeof(uint32_t) * t.total, s));
-    CT_CUDA(cudaMallocAsync((void**)&t.d_mean, sizeof(double) * n_jobs, s));
-    CT_CUDA(cudaMallocAsync((void**)&t.d_jev, sizeof(uint64_t) * n_jobs, s));
-    if (h_params) {
-        const size_t np = (size_t)params_per_trajectory(handles, n_jobs);
-        CT_CUDA(cudaMallocAsync((void**)&t.d_params, sizeof(float) * t.total * np, s));
-        CT_CUDA(cudaMemcpyAsync(t.d_params, h_params, sizeof(float) * t.total * np, cudaMemcpyHostToDevice, s));
-    }
-    int rc = ct_launch_rewards(eng, handles, n_traj, traj_base, job_cost, n_jobs, cfg, seed, s, t.d_params, t.d_reward,
-                               t.d_lag, t.d_events, nullptr, 0);
-    if (rc == CT_OK) rc = ct_reduce_jobs(eng, n_traj, n_jobs, s, t.d_reward, t.d_events, t.d_mean, t.d_jev);
+    int rc = submit_on_stream(eng, t, handles, n_traj, traj_base, job_cost, n_jobs, cfg, seed, h_params);
     if (rc != CT_OK) {
+        // (the buffers were released in stream order by submit_on_stream's scratch guard)
         cudaStreamSynchronize(s);
         cudaStreamDestroy(s);
         return rc;

@@ -17,7 +17,7 @@ import numpy as np
 
 from .grammar import CircuitGrammar
 
-__all__ = ["SimpleNetworkGrammar", "DimersGrammar"]
+__all__ = ["SimpleNetworkGrammar", "DimersGrammar", "SimpleNetworkTree", "DimerNetworkTree"]
 
 TERMINATE = "*terminate*"
 
@@ -471,3 +471,36 @@ class DimersGrammar(CircuitGrammar):
             if {x[:2] + x[3] for x in relabeled.split("_")} <= have:
                 return True
         return False
+
+
+def _tree_base():
+    from .circuitree import CircuiTree      # (circuitree.py looks grammars up in this module lazily)
+
+    return CircuiTree
+
+
+class SimpleNetworkTree(_tree_base()):
+    """``CircuiTree`` that builds its :class:`SimpleNetworkGrammar` from keyword arguments
+    (reference circuitree/models.py:483-521; default ``seed=2023`` as upstream).  ``get_reward`` is
+    still the subclass's to supply."""
+
+    def __init__(self, grammar: Optional[SimpleNetworkGrammar] = None, components=None, interactions=None,
+                 max_interactions: Optional[int] = None, root: Optional[str] = None, fixed_components=None, **tree_kwargs):
+        if grammar is None:
+            grammar = SimpleNetworkGrammar(components=components, interactions=interactions, max_interactions=max_interactions,
+                                           root=root, fixed_components=fixed_components)
+        tree_kwargs.setdefault("seed", 2023)
+        super().__init__(grammar=grammar, root=root, **tree_kwargs)
+
+
+class DimerNetworkTree(_tree_base()):
+    """``CircuiTree`` over a :class:`DimersGrammar` built from keyword arguments (reference
+    circuitree/models.py:942-980; default ``seed=2023`` as upstream)."""
+
+    def __init__(self, components, regulators, interactions, max_interactions: Optional[int] = None,
+                 max_interactions_per_promoter: int = 2, root: Optional[str] = None, **tree_kwargs):
+        grammar = DimersGrammar(components=components, regulators=regulators, interactions=interactions,
+                                max_interactions=max_interactions, max_interactions_per_promoter=max_interactions_per_promoter,
+                                root=root)
+        tree_kwargs.setdefault("seed", 2023)
+        super().__init__(grammar=grammar, root=root, **tree_kwargs)

@@ -17,10 +17,20 @@ from typing import Hashable, Optional, Sequence
 
 import numpy as np
 
-from . import _capi
+from . import _capi, _capi_defaults
 from .circuitree import CircuiTree
 
 __all__ = ["OscillationTree", "RewardEngine", "reward_landscape", "landscape_motifs"]
+
+
+def pairwise_shape(handles: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """(reactions R = 4 M + 2 edges, species M) of pairwise topology handles (SPEC.md section 2)."""
+    h = np.asarray(handles, dtype=np.uint64)
+    m = ((h >> np.uint64(56)) & np.uint64(15)).astype(np.int64)
+    edges = np.zeros(len(h), dtype=np.int64)
+    for c in range(25):
+        edges += ((h >> np.uint64(2 * c)) & np.uint64(3)) != 0
+    return 4 * m + 2 * edges, m
 
 
 class RewardEngine:
@@ -39,6 +49,7 @@ class RewardEngine:
         self.next_traj = 0           # trajectory ids handed out so far (fresh Philox streams per call)
         self.total_events = 0
         self.total_trajectories = 0
+        self.total_issue_slots = 0.0  # sum over pairwise jobs of events x I_step(R, M) (SPEC.md section 8): roofline numerator
         self.cost: dict[int, float] = {}   # topology handle -> events per trajectory observed so far
         self.share = 1               # asynchronous batches kept in flight: each gets 1/share of the CTA slots
 
@@ -72,15 +83,24 @@ class RewardEngine:
             bases = offsets + np.uint64(self.next_traj)
             self.next_traj += int(counts.sum())
         else:
+            # explicit ids (reward_landscape): later automatic ids start beyond them, so no stream is replayed
             bases = np.asarray(traj_base, dtype=np.uint64)
+            if len(bases):
+                self.next_traj = max(self.next_traj, int((bases + counts.astype(np.uint64)).max()))
         out = self.engine.rewards_host(handles, counts, bases, self.cfg, self.seed, params=params,
                                        per_trajectory=per_trajectory)
         self.total_events += int(out["job_events"].sum())
         self.total_trajectories += int(counts.sum())
+        self._count_issue_slots(handles, out["job_events"])
         out["n_traj"] = counts
         out["traj_base"] = bases
         return out
 
+
+    def _count_issue_slots(self, handles: np.ndarray, job_events: np.ndarray) -> None:
+        if len(handles) and not _capi.is_dimer_handle(int(handles[0])):
+            r, m = pairwise_shape(handles)
+            self.total_issue_slots += float((job_events.astype(np.float64) * _capi_defaults.i_step(r, m)).sum())
 
     # -- asynchronous batches of leaves (pipelined MCTS) ---------------------------------------------------
     def submit_leaves(self, handles: np.ndarray, trajectories_per_leaf: int) -> dict:
@@ -116,6 +136,7 @@ class RewardEngine:
         out = self.engine.wait(job["ticket"], per_trajectory=True)
         self.total_events += int(out["job_events"].sum())
         self.total_trajectories += int(job["n_traj"].sum())
+        self._count_issue_slots(job["uniq"], out["job_events"])
         for h, ev, nt in zip(job["uniq"], out["job_events"], job["n_traj"]):
             self.cost[int(h)] = float(ev) / float(nt)
         B = job["B"]
@@ -139,16 +160,26 @@ class OscillationTree(CircuiTree):
         device: CUDA device index (default ``LOCAL_RANK`` or 0).
         reward_seed: Philox key of the simulator (default: the tree's ``seed``).
         success_threshold: mean reward above which :meth:`is_success` is true (default 0.4).
+        next_traj: first unused trajectory id of the simulator stream.  ``to_file`` saves it next to
+            ``reward_seed`` and the numpy RNG state, so a tree restored with ``from_file`` continues
+            with fresh Philox streams instead of replaying the ones already used.
     """
 
     def __init__(self, *args, trajectories_per_reward: int = 32, sim_config=None, device: Optional[int] = None,
-                 reward_seed: Optional[int] = None, success_threshold: float = 0.4, **kwargs):
+                 reward_seed: Optional[int] = None, success_threshold: float = 0.4, next_traj: int = 0, **kwargs):
         super().__init__(*args, **kwargs)
         self.trajectories_per_reward = int(trajectories_per_reward)
         self.success_threshold = float(success_threshold)
         self.reward_seed = int(self.seed if reward_seed is None else reward_seed) & 0xFFFFFFFFFFFFFFFF
         self._reward_engine = RewardEngine(self.grammar, device=device, sim_config=sim_config, seed=self.reward_seed)
+        self._reward_engine.next_traj = int(next_traj)
         self._non_serializable_attrs.append("_reward_engine")
+
+    def get_attributes(self, attrs_copy=None) -> dict:
+        attrs = super().get_attributes(attrs_copy)
+        if attrs_copy is None or "next_traj" in attrs_copy:
+            attrs["next_traj"] = int(self._reward_engine.next_traj)
+        return attrs
 
     @property
     def reward_engine(self) -> RewardEngine:

@@ -126,6 +126,12 @@ int ct_rewards_host(ct_engine *eng, const uint64_t *handles, const uint32_t *n_t
  * into host buffers (each nullable) and releases the ticket.  Used by the pipelined MCTS
  * scheduler: leaves of batch k+1 are selected (under virtual loss, reference circuitree.py:532-535)
  * while batch k is still simulating.
+ * Lifetimes: handles / n_traj / traj_base / job_cost are consumed before submit returns.  h_params
+ * (nullable) is copied with cudaMemcpyAsync: pageable memory has been staged when submit returns, but
+ * PAGE-LOCKED (pinned) memory is read asynchronously and must stay valid and unmodified until
+ * ct_rewards_wait has returned for this ticket.  A ticket nobody waits for is released by
+ * ct_engine_destroy.  If submit fails, nothing stays allocated.  lpt launches take at most 2^31-1
+ * trajectories.
  */
 int ct_rewards_submit(ct_engine *eng, const uint64_t *handles, const uint32_t *n_traj,
                       const uint64_t *traj_base, const float *job_cost, int32_t n_jobs,

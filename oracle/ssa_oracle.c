@@ -173,7 +173,7 @@ typedef struct {
 static uint64_t simulate_pairwise(const uint8_t etype[CT_MAX_SPECIES][CT_MAX_SPECIES],
                                   const sim_cfg_t *cfg, const double *prm,
                                   uint64_t seed, uint64_t traj, rng_t *setup,
-                                  uint8_t *q /* [M][n_dec] */)
+                                  uint8_t *q /* [M][n_dec] */, double *final_state /* nullable [3][M] */)
 {
     const int M = cfg->n_species;
     const int n_dec = cfg->nt / cfg->decim;
@@ -256,6 +256,13 @@ static uint64_t simulate_pairwise(const uint8_t etype[CT_MAX_SPECIES][CT_MAX_SPE
         }
         ++n_events;
     }
+    if (final_state) {   /* state when the last grid sample was recorded: mRNA, free protein, molecules of j bound anywhere */
+        for (int j = 0; j < M; ++j) {
+            int bound = 0;
+            for (int t2 = 0; t2 < M; ++t2) bound += b[j][t2];
+            final_state[j] = R[j]; final_state[M + j] = P[j]; final_state[2 * M + j] = (double)bound;
+        }
+    }
     return n_events;
 }
 
@@ -265,6 +272,7 @@ typedef struct {
     const double *ranges, *explicit_params;
     uint64_t seed, traj_base; int64_t n_traj;
     float *reward; int32_t *lag; uint64_t *n_events; uint8_t *series; double *params_out;
+    double *final_state;
     atomic_llong next;
 } job_t;
 
@@ -285,7 +293,8 @@ static void *worker(void *arg)
             if (jb->explicit_params) memcpy(prm, jb->explicit_params + x * CT_N_PARAMS, sizeof prm);
             uint8_t qbuf[CT_MAX_SPECIES * 512];
             uint8_t *q = jb->series ? jb->series + (size_t)x * M * n_dec : qbuf;
-            uint64_t ne = simulate_pairwise(jb->etype, &jb->cfg, prm, jb->seed, traj, &setup, q);
+            uint64_t ne = simulate_pairwise(jb->etype, &jb->cfg, prm, jb->seed, traj, &setup, q,
+                                            jb->final_state ? jb->final_state + (size_t)x * 3 * M : NULL);
             int lg = 0;
             double rw = ct_oracle_reward_from_series(q, M, n_dec, &lg);
             if (jb->reward) jb->reward[x] = (float)rw;
@@ -303,6 +312,16 @@ static void *worker(void *arg)
  * [n_traj][10] overrides sampling.  Outputs (each nullable): reward[n_traj],
  * lag[n_traj] (decimated samples), n_events[n_traj], series[n_traj][M][n_dec],
  * params_out[n_traj][10].  Returns 0 on success.                            */
+int ct_oracle_run_pairwise_ex(int n_species,
+                           const int32_t *act, int n_act,
+                           const int32_t *inh, int n_inh,
+                           const double *ranges, const double *explicit_params,
+                           uint64_t seed, uint64_t traj_base, int64_t n_traj,
+                           int nt, int decim, double dt, double init_mean,
+                           int n_threads,
+                           float *reward, int32_t *lag, uint64_t *n_events,
+                           uint8_t *series, double *params_out, double *final_state);
+
 int ct_oracle_run_pairwise(int n_species,
                            const int32_t *act, int n_act,
                            const int32_t *inh, int n_inh,
@@ -312,6 +331,23 @@ int ct_oracle_run_pairwise(int n_species,
                            int n_threads,
                            float *reward, int32_t *lag, uint64_t *n_events,
                            uint8_t *series, double *params_out)
+{
+    return ct_oracle_run_pairwise_ex(n_species, act, n_act, inh, n_inh, ranges, explicit_params, seed, traj_base, n_traj,
+                                     nt, decim, dt, init_mean, n_threads, reward, lag, n_events, series, params_out, NULL);
+}
+
+/* Same, plus final_state (nullable) [n_traj][3][M]: mRNA counts, free protein counts and the number
+ * of molecules of each species bound at promoters when the last grid sample was recorded (used to
+ * check the simulator against exact master-equation moments, tests/test_oracle.py). */
+int ct_oracle_run_pairwise_ex(int n_species,
+                           const int32_t *act, int n_act,
+                           const int32_t *inh, int n_inh,
+                           const double *ranges, const double *explicit_params,
+                           uint64_t seed, uint64_t traj_base, int64_t n_traj,
+                           int nt, int decim, double dt, double init_mean,
+                           int n_threads,
+                           float *reward, int32_t *lag, uint64_t *n_events,
+                           uint8_t *series, double *params_out, double *final_state)
 {
     if (n_species < 1 || n_species > CT_MAX_SPECIES || nt < decim || decim < 1 || nt / decim > 512) return 1;
     uint8_t etype[CT_MAX_SPECIES][CT_MAX_SPECIES];
@@ -332,7 +368,7 @@ int ct_oracle_run_pairwise(int n_species,
     job.ranges = ranges; job.explicit_params = explicit_params;
     job.seed = seed; job.traj_base = traj_base; job.n_traj = n_traj;
     job.reward = reward; job.lag = lag; job.n_events = n_events;
-    job.series = series; job.params_out = params_out;
+    job.series = series; job.params_out = params_out; job.final_state = final_state;
     atomic_init(&job.next, 0);
     if (n_threads < 1) n_threads = 1;
     if (n_threads > 256) n_threads = 256;

@@ -46,6 +46,8 @@ def lib() -> ctypes.CDLL:
             ctypes.c_int,
             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
         ]
+        L.ct_oracle_run_pairwise_ex.restype = ctypes.c_int
+        L.ct_oracle_run_pairwise_ex.argtypes = L.ct_oracle_run_pairwise.argtypes + [ctypes.c_void_p]
         L.ct_oracle_run_dimers.restype = ctypes.c_int
         L.ct_oracle_run_dimers.argtypes = [
             ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
@@ -80,13 +82,14 @@ def _ptr(a):
 
 def run_pairwise(n_species, activations, inhibitions, ranges, n_traj, *, seed=0, traj_base=0,
                  explicit_params=None, nt=2000, decim=16, dt=20.0, init_mean=10.0,
-                 n_threads=1, want_series=False, want_params=False):
+                 n_threads=1, want_series=False, want_params=False, want_final=False):
     """Simulate ``n_traj`` trajectories of one pairwise topology.
 
     ``activations`` / ``inhibitions`` are the int[n,2] arrays returned by
     ``SimpleNetworkGrammar.parse_genotype`` (reference circuitree/models.py:441-480).
     Returns a dict with reward (f32), lag (i32, decimated samples), n_events (u64)
-    and optionally series (u8 [n_traj, n_species, nt//decim]) and params (f64).
+    and optionally series (u8 [n_traj, n_species, nt//decim]), params (f64) and final
+    (f64 [n_traj, 3, n_species]: mRNA, free protein, molecules bound at promoters at the end).
     """
     act = np.ascontiguousarray(np.asarray(activations, dtype=np.int32).reshape(-1, 2))
     inh = np.ascontiguousarray(np.asarray(inhibitions, dtype=np.int32).reshape(-1, 2))
@@ -100,10 +103,11 @@ def run_pairwise(n_species, activations, inhibitions, ranges, n_traj, *, seed=0,
     n_events = np.zeros(n_traj, dtype=np.uint64)
     series = np.zeros((n_traj, n_species, n_dec), dtype=np.uint8) if want_series else None
     params = np.zeros((n_traj, N_PARAMS), dtype=np.float64) if want_params else None
-    rc = lib().ct_oracle_run_pairwise(
+    final = np.zeros((n_traj, 3, n_species), dtype=np.float64) if want_final else None
+    rc = lib().ct_oracle_run_pairwise_ex(
         n_species, _ptr(act), act.shape[0], _ptr(inh), inh.shape[0],
         _ptr(rng), _ptr(exp), seed, traj_base, n_traj, nt, decim, dt, init_mean, n_threads,
-        _ptr(reward), _ptr(lag), _ptr(n_events), _ptr(series), _ptr(params))
+        _ptr(reward), _ptr(lag), _ptr(n_events), _ptr(series), _ptr(params), _ptr(final))
     if rc != 0:
         raise ValueError(f"ct_oracle_run_pairwise failed with code {rc}")
     out = {"reward": reward, "lag": lag, "n_events": n_events}
@@ -111,6 +115,8 @@ def run_pairwise(n_species, activations, inhibitions, ranges, n_traj, *, seed=0,
         out["series"] = series
     if want_params:
         out["params"] = params
+    if want_final:
+        out["final"] = final
     return out
 
 

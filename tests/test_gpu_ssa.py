@@ -128,6 +128,11 @@ TOPOLOGIES = [
     "*ABC::ABa_BCi_CAa",
     "*ABCD::ABi_BCi_CDi_DAi",
     "*ABCDE::ABi_BCi_CDi_DEi_EAi",
+    # promoters with an activator AND an inhibitor, and with two different regulators bound: the
+    # km_act_rep rate, the A_j bookkeeping and the mixed-regulator branch of the resolution block
+    "*ABC::AAa_ABi_BBa_BCi_CAi_CCa",     # top hit of the 3-component landscape
+    "*ABC::ABa_CBi_BCi_CAa",
+    "*ABCD::ABa_CBi_BCa_DCi_ADi_CAa_DDa",
 ]
 
 
@@ -144,6 +149,51 @@ def test_statistical_equivalence(eng, cfg, state):
     se_ev = np.sqrt(g["events"].var(ddof=1) / n + o["n_events"].astype(float).var(ddof=1) / n)
     z_ev = (g["events"].mean() - o["n_events"].mean()) / se_ev
     assert abs(z_ev) < 3.5, f"{state}: events/trajectory {g['events'].mean():.0f} vs {o['n_events'].mean():.0f} (z={z_ev:.2f})"
+
+
+def test_random_topology_sweep(eng):
+    """200 random terminal topologies (three and four components) x 1000 trajectories against the
+    recorded checker results (tests/golden/make_sweep_oracle.py; independent seeds): the per-topology
+    z-scores of mean reward and of events per trajectory must look like N(0,1) draws -- no outlier
+    beyond 4.5, Kolmogorov-Smirnov p > 0.01 -- and the pooled lag histogram must agree."""
+    from pathlib import Path
+
+    gold = np.load(Path(__file__).parent / "golden" / "sweep_oracle.npz")
+    states = [str(s) for s in gold["states"]]
+    n = 1000
+    c = small_cfg(nt=640, decim=16)
+    g = gpu_run(eng, states, n, c, seed=777)
+    rw = g["reward"].astype(np.float64).reshape(len(states), n)
+    ev = g["events"].astype(np.float64).reshape(len(states), n)
+    z_r = (rw.mean(axis=1) - gold["reward_mean"]) / np.sqrt(rw.var(axis=1, ddof=1) / n + gold["reward_var"] / n)
+    z_e = (ev.mean(axis=1) - gold["events_mean"]) / np.sqrt(ev.var(axis=1, ddof=1) / n + gold["events_var"] / n)
+    for name, z in (("reward", z_r), ("events", z_e)):
+        assert np.abs(z).max() < 4.5, (name, states[int(np.abs(z).argmax())], float(np.abs(z).max()))
+        p = stats.kstest(z, "norm").pvalue
+        assert p > 0.01, f"{name}: z-scores are not N(0,1): KS p={p:.4f}, mean {z.mean():.3f}, sd {z.std():.3f}"
+        assert abs(z.mean()) < 4.0 / np.sqrt(len(z)), f"{name}: systematic shift, mean z = {z.mean():.3f}"
+    lag_hist = np.bincount(g["lag"], minlength=gold["lag_hist"].shape[1])
+    gold_hist = gold["lag_hist"].sum(axis=0)
+    keep = (lag_hist + gold_hist) >= 10
+    chi = stats.chi2_contingency(np.vstack([lag_hist[keep], gold_hist[keep]]))
+    assert chi.pvalue > 0.01, f"pooled lag histograms differ: p={chi.pvalue:.4f}"
+
+
+def test_event_count_has_no_bias_at_high_power(eng):
+    """2^20 trajectories on a short grid, same streams on both sides (paired): float32 arithmetic,
+    lg2.approx / rcp.approx in tau and the float32 time-to-next-sample accumulation must not shift
+    the number of events per trajectory by more than 5e-4 (relative), for a single-regulator topology
+    (specialised loop) and for one with mixed promoters (general loop)."""
+    n = 1 << 20
+    c = small_cfg(nt=64, decim=16)
+    for state in ("*ABC::ABi_BCi_CAi", "*ABC::AAa_ABi_BBa_BCi_CAi_CCa"):
+        g = gpu_run(eng, [state], n, c, seed=31)
+        o = oracle_run(state, n, c, seed=31)
+        d = g["events"].astype(np.float64) - o["n_events"].astype(np.float64)
+        rel = d.mean() / o["n_events"].mean()
+        assert abs(rel) < 5e-4, f"{state}: events/trajectory biased by {rel:.2e} (gpu {g['events'].mean():.2f}, cpu {o['n_events'].mean():.2f})"
+        # the paired differences are what float32 rounding does to individual trajectories: small and centred
+        assert abs(d.mean()) < 5.0 * d.std(ddof=1) / np.sqrt(n) + 1e-4 * o["n_events"].mean()
 
 
 def test_same_stream_trajectories_track_the_checker(eng, cfg):

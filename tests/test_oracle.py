@@ -186,3 +186,85 @@ def test_unregulated_gene_matches_birth_death_theory():
     rate = 2.0 * km * (1.0 + kp / gm)
     expected = rate * (T - relax) + rate * relax * 0.5  # ramp-up from an (almost) empty cell
     assert abs(o["n_events"].mean() - expected) / expected < 0.02
+
+
+# ---- external anchor that exercises promoter binding: exact moments of promoter-switching models ----
+def switching_moments(Q, k, gamma):
+    """Exact stationary mean and variance of a birth-death species whose production rate k[s]
+    follows a finite Markov chain s(t) with generator Q (rows sum to 0), degraded at rate gamma.
+    Standard moment equations of the master equation: with pi the stationary law of s and
+    m_s = E[R 1{s}],  0 = Q^T m + k*pi - gamma m,  E[R(R-1)] = sum_s k_s m_s / gamma.
+    For two states this is the telegraph model of Peccoud & Ycart (1995)."""
+    Q = np.asarray(Q, dtype=float); k = np.asarray(k, dtype=float)
+    n = len(k)
+    A = np.vstack([Q.T, np.ones(n)])
+    pi = np.linalg.lstsq(A, np.concatenate([np.zeros(n), [1.0]]), rcond=None)[0]
+    m = np.linalg.solve(gamma * np.eye(n) - Q.T, k * pi)
+    mean = m.sum()
+    var = (k * m).sum() / gamma + mean - mean ** 2
+    return mean, var
+
+
+def test_switching_moments_reduce_to_the_telegraph_closed_form():
+    a, b, k0, k1, g = 0.03, 0.2, 1.0, 0.05, 0.02          # unbound -> bound at a, back at b
+    mean, var = switching_moments([[-a, a], [b, -b]], [k0, k1], g)
+    p_u = b / (a + b)
+    mean_cf = (k0 * p_u + k1 * (1 - p_u)) / g
+    var_cf = mean_cf + (k0 - k1) ** 2 * p_u * (1 - p_u) / (g * (g + a + b))
+    assert abs(mean - mean_cf) < 1e-9 * mean_cf and abs(var - var_cf) < 1e-9 * var_cf
+
+
+def _telegraph_run(n_species, act, inh, prm, n, seed):
+    # k_p = gamma_p = 0 freezes every protein count at its Poisson(1) initial value except for
+    # (un)binding, so a regulator that starts with ONE molecule toggles one promoter site:
+    # binding 0 -> 1 at k_on * 1 * (2 - 0), no second binding (no free molecule left), unbinding at k_off1.
+    params = np.tile(np.asarray(prm, dtype=np.float64), (n, 1))
+    out = so.run_pairwise(n_species, act, inh, RANGES, n, seed=seed, explicit_params=params, nt=500, decim=20, dt=20.0,
+                          init_mean=1.0, n_threads=so.max_threads(), want_final=True)
+    f = out["final"]
+    return f[:, 0, :], f[:, 1, :] + f[:, 2, :]           # final mRNA counts, conserved protein totals
+
+
+def _check_moments(r, mean, var, label):
+    n = len(r)
+    assert n > 3000, (label, n)
+    se_mean = np.sqrt(var / n)
+    assert abs(r.mean() - mean) < 4.0 * se_mean, (label, r.mean(), mean)
+    # the sample variance of n values has standard error ~ var * sqrt((kurt - 1) / n); these
+    # over-dispersed counts stay below kurtosis 4.5, so 4 s.e. is within 7.5 % at n > 10^4 / 4
+    assert abs(r.var(ddof=1) - var) < 4.0 * var * np.sqrt(3.5 / n), (label, r.var(ddof=1), var)
+    assert var / mean > 1.5, "the test must be sensitive to promoter noise (Fano factor well above Poisson)"
+
+
+def test_promoter_binding_matches_exact_telegraph_moments():
+    """Pins the checker's binding / unbinding / regulated-transcription arithmetic to an external
+    result (SPEC.md section 2): mean and Fano factor of the target's mRNA for an inhibitor and for an
+    activator with a single molecule (two-state telegraph), and for one activator plus one inhibitor
+    molecule competing for the two sites (four promoter states, all four transcription rates)."""
+    k_on, k_off1, k_off2 = 0.004, 0.012, 0.005
+    km0, km_a, km_r, km_ar = 0.4, 1.5, 0.02, 0.15
+    gm = 0.02
+    prm = [k_on, k_off1, k_off2, km0, km_a, km_r, km_ar, 0.0, gm, 0.0]
+    a, b = 2 * k_on, k_off1
+    # A inhibits B
+    r, tot = _telegraph_run(2, [], [(0, 1)], prm, 40_000, seed=71)
+    mean, var = switching_moments([[-a, a], [b, -b]], [km0, km_r], gm)
+    _check_moments(r[tot[:, 0] == 1, 1], mean, var, "inhibitor")
+    # the unregulated gene A is a plain birth-death process: Poisson with mean km0 / gm
+    assert abs(r[:, 0].mean() - km0 / gm) < 4 * np.sqrt(km0 / gm / len(r))
+    assert abs(r[:, 0].var(ddof=1) / r[:, 0].mean() - 1.0) < 0.05
+    # A activates B
+    r, tot = _telegraph_run(2, [(0, 1)], [], prm, 40_000, seed=72)
+    mean, var = switching_moments([[-a, a], [b, -b]], [km0, km_a], gm)
+    _check_moments(r[tot[:, 0] == 1, 1], mean, var, "activator")
+    # A activates C, B inhibits C, one molecule each: promoter states (bA, bB) = 00, 10, 01, 11
+    r, tot = _telegraph_run(3, [(0, 2)], [(1, 2)], prm, 120_000, seed=73)
+    Q = np.zeros((4, 4))
+    Q[0, 1] = 2 * k_on; Q[0, 2] = 2 * k_on          # first molecule: two free sites
+    Q[1, 3] = k_on; Q[2, 3] = k_on                  # second molecule: one free site
+    Q[1, 0] = k_off1; Q[2, 0] = k_off1              # n = 1: k_off1 per bound molecule
+    Q[3, 1] = k_off2; Q[3, 2] = k_off2              # n = 2: k_off2 per bound molecule (B leaves -> 10, A leaves -> 01)
+    Q -= np.diag(Q.sum(axis=1))
+    mean, var = switching_moments(Q, [km0, km_a, km_r, km_ar], gm)
+    sel = (tot[:, 0] == 1) & (tot[:, 1] == 1)
+    _check_moments(r[sel, 2], mean, var, "activator + inhibitor")
