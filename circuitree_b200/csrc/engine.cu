@@ -15,6 +15,7 @@
 #include "../../include/circuitree_b200.h"
 #include "ssa_pairwise.cuh"
 #include "ssa_dimers.cuh"
+#include "ssa_dimers_coop.cuh"
 
 namespace {
 
@@ -86,6 +87,10 @@ inline int params_per_trajectory(const uint64_t* handles, int n_jobs)
 }  // namespace
 
 namespace {
+// automatic schedule: dimer launches of up to this many times the resident one-lane-per-trajectory
+// lanes run on the cooperative kernel (measured switch-over)
+constexpr int kCoopAutoFactor = 2;
+
 struct Ticket {                      // one asynchronous reward batch in flight
     cudaStream_t stream = nullptr;
     int32_t n_jobs = 0;
@@ -117,7 +122,8 @@ namespace {
 template <int MM, bool kMixed, bool kAll, bool kFast = false>
 int prepare_kernel(KernelInfo& ki)
 {
-    ki.smem = (size_t)ct::kThreads * MM * ct::kSerStride + (ct::kThreads / 32) * ct::kSerStride * sizeof(float);
+    // per warp: reward scratch + the staging copy of one finished record (the records themselves live in global scratch)
+    ki.smem = (size_t)(ct::kThreads / 32) * (ct::kSerStride * sizeof(float) + (size_t)MM * ct::kSerStride);
     CT_CUDA(cudaFuncSetAttribute(ct::ssa_pairwise_kernel<MM, kMixed, kAll, kFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
     CT_CUDA(cudaFuncSetAttribute(ct::ssa_pairwise_kernel<MM, kMixed, kAll, kFast>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared));
@@ -134,7 +140,8 @@ int validate_cfg(const ct_sim_config* cfg)
     if (cfg->nt / cfg->decim > CT_MAX_NDEC) return fail(CT_ERR_INVALID, "nt/decim = %d exceeds CT_MAX_NDEC", cfg->nt / cfg->decim);
     if (!(cfg->dt > 0.0f)) return fail(CT_ERR_INVALID, "dt must be positive");
     if (!(cfg->init_mean >= 0.0f) || cfg->init_mean > 80.0f) return fail(CT_ERR_INVALID, "init_mean out of range [0, 80]");
-    if (cfg->schedule < 0 || cfg->schedule > 2) return fail(CT_ERR_INVALID, "schedule must be 0 (auto), 1 (uniform) or 2 (mixed)");
+    if (cfg->schedule < 0 || cfg->schedule > 3)
+        return fail(CT_ERR_INVALID, "schedule must be 0 (auto), 1 (uniform), 2 (mixed) or 3 (cooperative)");
     if (cfg->lpt < 0 || cfg->lpt > 1) return fail(CT_ERR_INVALID, "lpt must be 0 or 1");
     if (cfg->grid_limit < 0) return fail(CT_ERR_INVALID, "grid_limit must be >= 0");
     if (cfg->fast_path < 0 || cfg->fast_path > 1) return fail(CT_ERR_INVALID, "fast_path must be 0 or 1");
@@ -212,6 +219,13 @@ int ct_engine_create(int device, ct_engine** out)
                                               (int)(big.warp_bytes() * (ct::kDimThreads / 32)));
         cudaError_t e5 = cudaFuncSetAttribute(ct::ssa_dimers_mixed_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                               cudaSharedmemCarveoutMaxShared);
+        const int coop8 = (int)(ct::coop_warp_bytes(8, ct::kMaxSpecies) * (ct::kCoopThreads / 32));
+        const int coop4 = (int)(ct::coop_warp_bytes(4, 3) * (ct::kCoopThreads / 32));
+        if (cudaFuncSetAttribute(ct::ssa_dimers_coop_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, coop8) != cudaSuccess ||
+            cudaFuncSetAttribute(ct::ssa_dimers_coop_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, coop4) != cudaSuccess ||
+            cudaFuncSetAttribute(ct::ssa_dimers_coop_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess ||
+            cudaFuncSetAttribute(ct::ssa_dimers_coop_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+            e1 = cudaErrorUnknown;
         if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess ||
             ki.blocks_per_sm < 1) {
             delete eng;
@@ -441,12 +455,16 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
     // the jobs are much larger than the machine (a warp that has to change topology drains first);
     // measured on the 3-component landscape (419 jobs x 10^4 trajectories): 5.7e10 steps/s one
     // topology per warp, 1.3e11 mixed.
-    bool mixed = cfg->schedule == 2;
-    if (cfg->schedule == 0) {
-        const uint64_t resident = (uint64_t)eng->n_sm * eng->ki[0][0][1].blocks_per_sm * ct::kThreads;
-        mixed = n_jobs > 1 && total / (uint64_t)n_jobs < 4 * resident;
-    }
+    bool mixed = cfg->schedule == 2 || cfg->schedule == 3;
+    const uint64_t resident = (uint64_t)eng->n_sm * eng->ki[0][0][1].blocks_per_sm * ct::kThreads;
+    if (cfg->schedule == 0) mixed = n_jobs > 1 && total / (uint64_t)n_jobs < 4 * resident;
     if (dimers && !lane_progs_ok) mixed = false;   // per-lane programs need <= kMixK interactions per promoter
+    // Dimer launches that cannot give every resident lane a trajectory of its own -- MCTS batches, single
+    // get_reward calls -- last as long as their longest trajectory: spread each trajectory over a sub-group
+    // of lanes instead (ssa_dimers_coop.cuh; identical results).
+    bool coop = dimers && lane_progs_ok && cfg->schedule == 3;
+    if (dimers && lane_progs_ok && cfg->schedule == 0) coop = total <= (uint64_t)kCoopAutoFactor * resident;
+    if (coop) mixed = true;                        // (launch positions, not per-job tiles)
     if (mixed) A.n_tiles = (uint32_t)((total + ct::kTile - 1) / ct::kTile);   // tiles over launch positions
 
     // longest-expected-first order (cfg->lpt): cost pre-pass + radix sort of (job, cost) keys
@@ -485,6 +503,25 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
         const size_t prog_bytes = mixed ? sizeof(ct::DimerLaneProg) * lane_progs.size() : sizeof(ct::DimerProg) * progs.size();
         CT_CUDA(scratch.alloc(&d_progs, prog_bytes));
         CT_CUDA(cudaMemcpyAsync(d_progs, h_progs, prog_bytes, cudaMemcpyHostToDevice, stream));
+        if (coop) {
+            const int G = (shape.n_tf <= 3 && shape.n_dim <= 4) ? 4 : 8;
+            const int ser_species = shape.n_tf;
+            const size_t csmem = ct::coop_warp_bytes(G, ser_species) * (ct::kCoopThreads / 32);
+            int per_sm = 0;
+            if (G == 8) CT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ct::ssa_dimers_coop_kernel<8>, ct::kCoopThreads, csmem));
+            else CT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ct::ssa_dimers_coop_kernel<4>, ct::kCoopThreads, csmem));
+            if (per_sm < 1) return fail(CT_ERR_CUDA, "cooperative dimer kernel does not fit on an SM (%zu bytes of shared memory)", csmem);
+            const uint64_t per_cta = (uint64_t)ct::kCoopThreads / G;            // trajectories a CTA runs at a time
+            const uint64_t want = (total + per_cta - 1) / per_cta;
+            uint64_t cap = (uint64_t)eng->n_sm * per_sm;
+            if (cfg->grid_limit > 0 && (uint64_t)cfg->grid_limit < cap) cap = (uint64_t)cfg->grid_limit;
+            const unsigned cgrid = (unsigned)(want < cap ? want : cap);
+            if (G == 8) ct::ssa_dimers_coop_kernel<8><<<cgrid, ct::kCoopThreads, csmem, stream>>>(A, (const ct::DimerLaneProg*)d_progs, ser_species);
+            else ct::ssa_dimers_coop_kernel<4><<<cgrid, ct::kCoopThreads, csmem, stream>>>(A, (const ct::DimerLaneProg*)d_progs, ser_species);
+            CT_CUDA(cudaGetLastError());
+            eng->launches += 1;
+            return CT_OK;
+        }
         const size_t smem = (mixed ? shape.warp_bytes() : lay.warp_bytes()) * (ct::kDimThreads / 32);
         const size_t rec_lane = mixed ? shape.rec_lane_bytes() : lay.rec_lane_bytes();
         int per_sm = 0;
@@ -525,6 +562,8 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
     uint64_t max_blocks = (uint64_t)eng->n_sm * ki.blocks_per_sm;
     if (cfg->grid_limit > 0 && (uint64_t)cfg->grid_limit < max_blocks) max_blocks = (uint64_t)cfg->grid_limit;
     const unsigned grid = (unsigned)(want_blocks < max_blocks ? want_blocks : max_blocks);
+    // per-lane record scratch: mm x 128 bytes per resident lane (a byte per species every `decim` grid points)
+    CT_CUDA(scratch.alloc(&A.records, (size_t)grid * ct::kThreads * mm * ct::kSerStride));
 #define CT_LAUNCH(MM, MIXED, ALL) ct::ssa_pairwise_kernel<MM, MIXED, ALL><<<grid, ct::kThreads, ki.smem, stream>>>(A)
 #define CT_LAUNCH_M(MM)                                                          \
     do {                                                                         \

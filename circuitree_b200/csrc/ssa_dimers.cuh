@@ -24,6 +24,8 @@
 #pragma once
 #include <string.h>
 
+#include <algorithm>
+
 #include "ssa_pairwise.cuh"
 
 namespace ct {
@@ -50,7 +52,7 @@ struct DimerProg {                  // 272 bytes, one per job
     uint32_t pk_ix_start;           // TF s owns sorted interactions [start(s), start(s+1)), start(s) at bits 4s (s = 0..5)
     uint32_t pk_dim_a, pk_dim_b;    // monomers of dimer d at bits 3d
     uint8_t n_tf, n_ixn, n_dim, n_entries;
-    uint8_t search_iters;           // ceil(log2(n_entries + 1))
+    uint8_t search_iters;           // ceil(log2(longest block + 1)): trip count of the search inside a block
     uint8_t pad[3];
     // reaction -> 4 x (slot | code << 6) on distinct slots; code 0 = +1, 1 = -1, 2 = +2, 3 = -2
     // (a dummy slot absorbs unused fields); entry n_entries = "no reaction"
@@ -112,8 +114,10 @@ inline DimerProg dimer_program(const DimerTopo& T)
     }
     G.n_entries = (uint8_t)r;
     G.stoich[r] = word((uint32_t)kSlotDummy);
+    int longest = 8;                                   // a block of four dimers
+    for (int s = 0; s < T.n_tf; ++s) longest = std::max(longest, 4 + 2 * (start[s + 1] - start[s]));
     int it = 0;
-    while ((1 << it) < r + 1) ++it;
+    while ((1 << it) < longest + 1) ++it;
     G.search_iters = (uint8_t)it;
     return G;
 }
@@ -301,8 +305,11 @@ __global__ void __launch_bounds__(kDimThreads, 10) ssa_dimers_kernel(const Launc
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
             const uint32_t w_tau = h ? x.w[2] : x.w[0], w_sel = h ? x.w[3] : x.w[1];
-            // ---- pass 1: running sum of propensities in SPEC order, every partial sum stored ----
-            float c = 0.0f;
+            // ---- pass 1: block-wise running sums in SPEC order (section 9): one block per TF, one per four
+            // dimers; every block starts at zero, every partial sum is stored, the block totals are added up
+            // in block order (oe[b] = end offset of block b; an absent block adds an exact 0) ----
+            float osum = 0.0f;
+            float oe[kMaxSpecies + 3];
             float* cp = cum;
 #pragma unroll
             for (int s = 0; s < kMaxSpecies; ++s) {
@@ -311,7 +318,7 @@ __global__ void __launch_bounds__(kDimThreads, 10) ssa_dimers_kernel(const Launc
                     const float r = X[(kSlotR + s) * 32], p = X[(kSlotP + s) * 32];
                     const float km_a = (na > 0.0f) ? km1 : km0;
                     const float km_i = (na > 0.0f) ? km3 : km2;
-                    c += (n > na) ? km_i : km_a;    cp[0] = c;
+                    float c = (n > na) ? km_i : km_a;   cp[0] = c;
                     c = fmaf(gm, r, c);             cp[32] = c;
                     c = fmaf(kp, r, c);             cp[64] = c;
                     c = fmaf(gp, p, c);             cp[96] = c;
@@ -328,18 +335,27 @@ __global__ void __launch_bounds__(kDimThreads, 10) ssa_dimers_kernel(const Launc
 #pragma unroll 1
                         for (int q = x0; q < x1; ++q) { c = fmaf(koff, X[(kSlotB + q) * 32], c); *cp = c; cp += 32; }
                     }
+                    osum += c;
                 }
+                oe[s] = osum;
             }
+#pragma unroll
+            for (int gq = 0; gq < 3; ++gq) {
+                float c = 0.0f;
+                const int d_end = min(n_dim, 4 * gq + 4);
 #pragma unroll 1
-            for (int d = 0; d < n_dim; ++d) {
-                const int da = (pk_dim_a >> (3 * d)) & 7, db = (pk_dim_b >> (3 * d)) & 7;
-                const float pa = X[(kSlotP + da) * 32], pb = X[(kSlotP + db) * 32];
-                const float pairs = (da != db) ? pa * pb : 0.5f * pa * (pa - 1.0f);
-                c = fmaf(k_dim, pairs, c);                      cp[0] = c;
-                c = fmaf(k_undim, X[(kSlotD + d) * 32], c);     cp[32] = c;
-                cp += 64;
+                for (int d = 4 * gq; d < d_end; ++d) {
+                    const int da = (pk_dim_a >> (3 * d)) & 7, db = (pk_dim_b >> (3 * d)) & 7;
+                    const float pa = X[(kSlotP + da) * 32], pb = X[(kSlotP + db) * 32];
+                    const float pairs = (da != db) ? pa * pb : 0.5f * pa * (pa - 1.0f);
+                    c = fmaf(k_dim, pairs, c);                      cp[0] = c;
+                    c = fmaf(k_undim, X[(kSlotD + d) * 32], c);     cp[32] = c;
+                    cp += 64;
+                }
+                osum += c;
+                oe[kMaxSpecies + gq] = osum;
             }
-            const float a0 = c;
+            const float a0 = osum;
 
             // ---- time to next event; grid samples crossed keep the pre-event state ----
             const float tau = (-0.69314718056f * fast_log2(u01(w_tau))) * fast_rcp(a0);   // a0 == 0 -> +inf
@@ -368,15 +384,36 @@ __global__ void __launch_bounds__(kDimThreads, 10) ssa_dimers_kernel(const Launc
 
             // ---- pass 2: each lane finds its reaction (first partial sum above the target) and fires it ----
             const float target = alive ? u01(w_sel) * a0 : 3.0e38f;
-            int lo = 0, hi = n_entries;
+            // the block whose offsets bracket the target, then the first entry of that block whose local sum exceeds
+            // the target's position inside the block; rounding can leave none: nothing fires (SPEC.md section 2)
+            int bl = 0;
+            float off = 0.0f;
+#pragma unroll
+            for (int b = 0; b < kMaxSpecies + 3; ++b) {
+                const bool below = oe[b] <= target;
+                bl += below ? 1 : 0;
+                off = below ? oe[b] : off;
+            }
+            const float tl = target - off;
+            const int tf_end = 4 * n_tf + 2 * (int)((pk_ix_start >> (4 * kMaxSpecies)) & 15u);
+            int lo, hi;
+            if (bl < kMaxSpecies) {
+                lo = 4 * bl + 2 * (int)((pk_ix_start >> (4 * bl)) & 15u);
+                hi = 4 * bl + 4 + 2 * (int)((pk_ix_start >> (4 * bl + 4)) & 15u);
+            } else {
+                lo = min(tf_end + 8 * (bl - kMaxSpecies), n_entries);
+                hi = min(lo + 8, n_entries);
+            }
+            const int blk_end = hi;
 #pragma unroll 1
             for (int it = 0; it < search_iters; ++it) {
                 const int mid = (lo + hi) >> 1;
-                const bool lt = target < cum[mid * 32];
+                const bool open = lo < hi;
+                const bool lt = open && (tl < cum[mid * 32]);
                 hi = lt ? mid : hi;
-                lo = lt ? lo : mid + 1;
+                lo = (open && !lt) ? mid + 1 : lo;
             }
-            const uint32_t sw = G->stoich[lo];
+            const uint32_t sw = G->stoich[(lo < blk_end) ? lo : n_entries];
             // the four fields name distinct slots: load all, then store all
             float* f0 = X + (sw & 63u) * 32;
             float* f1 = X + ((sw >> 8) & 63u) * 32;
@@ -473,7 +510,7 @@ __global__ void __launch_bounds__(kDimThreads, 8) ssa_dimers_mixed_kernel(const 
     const size_t ser_lane_bytes = shape.rec_lane_bytes();
     uint8_t* warp_ser = records + ((size_t)blockIdx.x * (kDimThreads / 32) + warp) * 32 * ser_lane_bytes;
     uint8_t* ser = warp_ser + (size_t)lane * ser_lane_bytes;
-    const int ntf_max = shape.n_tf, nd_max = shape.n_dim, n_entries = shape.n_entries, search_iters = shape.search_iters;
+    const int ntf_max = shape.n_tf, nd_max = shape.n_dim, n_entries = shape.n_entries;
     const int tf_entries = ntf_max * kMixPerTf;
 
     float k_on = 0.f, k_on2 = 0.f, k_off1 = 0.f, k_off2 = 0.f, km0 = 0.f, km1 = 0.f, km2 = 0.f, km3 = 0.f, kp = 0.f, gm = 0.f,
@@ -591,8 +628,11 @@ __global__ void __launch_bounds__(kDimThreads, 8) ssa_dimers_mixed_kernel(const 
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
             const uint32_t w_tau = h ? x.w[2] : x.w[0], w_sel = h ? x.w[3] : x.w[1];
-            // ---- pass 1: the launch-wide reaction list; what this lane's topology lacks contributes an exact 0 ----
-            float c = 0.0f;
+            // ---- pass 1: the launch-wide reaction list, block-wise (SPEC.md section 9: one block per TF, one per four
+            // dimers, every block starts at zero, totals added in block order); what this lane's topology lacks
+            // contributes an exact 0 ----
+            float osum = 0.0f;
+            float oe[kMaxSpecies + 3];
             float* cp = cum;
 #pragma unroll
             for (int s = 0; s < kMaxSpecies; ++s) {
@@ -602,7 +642,7 @@ __global__ void __launch_bounds__(kDimThreads, 8) ssa_dimers_mixed_kernel(const 
                     const float km_a = (na > 0.0f) ? km1 : km0;
                     const float km_i = (na > 0.0f) ? km3 : km2;
                     const float km = (n > na) ? km_i : km_a;
-                    c += (s < n_tf) ? km : 0.0f;    cp[0] = c;      // (a TF this lane does not have: no transcription)
+                    float c = (s < n_tf) ? km : 0.0f;    cp[0] = c;      // (a TF this lane does not have: no transcription)
                     c = fmaf(gm, r, c);             cp[32] = c;
                     c = fmaf(kp, r, c);             cp[64] = c;
                     c = fmaf(gp, p, c);             cp[96] = c;
@@ -620,18 +660,27 @@ __global__ void __launch_bounds__(kDimThreads, 8) ssa_dimers_mixed_kernel(const 
                         c = fmaf(koff, X[(kSlotB + kMixK * s + q) * 32], c);    cp[(4 + kMixK + q) * 32] = c;
                     }
                     cp += kMixPerTf * 32;
+                    osum += c;
                 }
+                oe[s] = osum;
             }
+#pragma unroll
+            for (int gq = 0; gq < 3; ++gq) {
+                float c = 0.0f;
+                const int d_end = min(nd_max, 4 * gq + 4);
 #pragma unroll 1
-            for (int d = 0; d < nd_max; ++d) {
-                const uint32_t da = (dma >> (3 * d)) & 7u, db = (dmb >> (3 * d)) & 7u;
-                const float pa = X[(kSlotP + da) * 32], pb = X[(kSlotP + db) * 32];
-                const float pairs = (da != db) ? pa * pb : 0.5f * pa * (pa - 1.0f);
-                c = fmaf(((dmask >> d) & 1u) ? k_dim : 0.0f, pairs, c);     cp[0] = c;
-                c = fmaf(k_undim, X[(kSlotD + d) * 32], c);                  cp[32] = c;
-                cp += 64;
+                for (int d = 4 * gq; d < d_end; ++d) {
+                    const uint32_t da = (dma >> (3 * d)) & 7u, db = (dmb >> (3 * d)) & 7u;
+                    const float pa = X[(kSlotP + da) * 32], pb = X[(kSlotP + db) * 32];
+                    const float pairs = (da != db) ? pa * pb : 0.5f * pa * (pa - 1.0f);
+                    c = fmaf(((dmask >> d) & 1u) ? k_dim : 0.0f, pairs, c);     cp[0] = c;
+                    c = fmaf(k_undim, X[(kSlotD + d) * 32], c);                  cp[32] = c;
+                    cp += 64;
+                }
+                osum += c;
+                oe[kMaxSpecies + gq] = osum;
             }
-            const float a0 = c;
+            const float a0 = osum;
 
             // ---- time to next event; grid samples crossed keep the pre-event state ----
             const float tau = (-0.69314718056f * fast_log2(u01(w_tau))) * fast_rcp(a0);   // a0 == 0 -> +inf
@@ -660,14 +709,30 @@ __global__ void __launch_bounds__(kDimThreads, 8) ssa_dimers_mixed_kernel(const 
 
             // ---- pass 2: find the reaction (first partial sum above the target), derive its stoichiometry, fire ----
             const float target = alive ? u01(w_sel) * a0 : 3.0e38f;
-            int lo = 0, hi = n_entries;
-#pragma unroll 1
-            for (int it = 0; it < search_iters; ++it) {
-                const int mid = (lo + hi) >> 1;
-                const bool lt = target < cum[mid * 32];
-                hi = lt ? mid : hi;
-                lo = lt ? lo : mid + 1;
+            // the block whose offsets bracket the target, then the first of its (at most eight) entries whose local
+            // sum exceeds the target's position inside the block; none (rounding): nothing fires
+            int bl = 0;
+            float off = 0.0f;
+#pragma unroll
+            for (int b = 0; b < kMaxSpecies + 3; ++b) {
+                const bool below = oe[b] <= target;
+                bl += below ? 1 : 0;
+                off = below ? oe[b] : off;
             }
+            const float tl = target - off;
+            int lo = (bl < kMaxSpecies) ? kMixPerTf * bl : tf_entries + 8 * (bl - kMaxSpecies);
+            lo = min(lo, n_entries);
+            int hi = min(lo + 8, n_entries);
+            const int blk_end = hi;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int mid = (lo + hi) >> 1;
+                const bool open = lo < hi;
+                const bool lt = open && (tl < cum[mid * 32]);
+                hi = lt ? mid : hi;
+                lo = (open && !lt) ? mid + 1 : lo;
+            }
+            lo = (lo < blk_end) ? lo : n_entries;
             // four (slot, delta) fields on distinct slots; unused fields sit on the four dummies
             int s0 = kSlotDummy, s1 = kSlotDummy + 1, s2 = kSlotDummy + 2, s3 = kSlotDummy + 3;
             float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;

@@ -1,8 +1,12 @@
 // Batched Gillespie SSA + in-kernel oscillation reward for the pairwise TF-network model
 // (SPEC.md sections 2-8).  One trajectory per lane, one topology per warp at a time, persistent
 // warps that pull 32-trajectory tiles off a global counter and refill lanes as trajectories end.
-// The per-trajectory record (M x n_dec companded bytes) lives in shared memory and is reduced to
-// (reward, lag) by the whole warp with shuffles when the lane finishes; it never reaches HBM.
+// The per-trajectory record (M x n_dec companded bytes, one byte per species every `decim` grid
+// points) is parked in a per-lane scratch area in global memory -- a few hundred bytes written
+// over ~10^5 events, L2-resident -- and staged back into shared memory when the lane finishes,
+// where the whole warp reduces it to (reward, lag) with shuffles.  Keeping it in shared memory
+// (round 1: 384 bytes per lane for M = 3) capped residency at 4 CTAs per SM; now registers alone
+// decide (launch bounds below), and the full trajectories still never exist anywhere.
 //
 // Reference boundary: this is what get_reward (reference circuitree/circuitree.py:135-152)
 // computes for the topology parse_genotype (reference circuitree/models.py:441-480) describes.
@@ -19,6 +23,17 @@
 // block's steps (+-0 %).
 #ifndef CT_UNROLL_H
 #define CT_UNROLL_H 1         // 1: the two steps of a Philox block are unrolled into one basic block
+#endif
+// Resident CTAs per SM the compiler has to make room for (registers per thread <= 65536 / (128 * n)),
+// for M = 3, 4, 5.  Measured on B200 (profiles/r02_*): see there for the choice.
+#ifndef CT_MINB3
+#define CT_MINB3 5
+#endif
+#ifndef CT_MINB4
+#define CT_MINB4 4
+#endif
+#ifndef CT_MINB5
+#define CT_MINB5 4
 #endif
 
 namespace ct {
@@ -49,6 +64,7 @@ struct LaunchArgs {
     float* reward;
     int32_t* lag;                    // nullable
     uint32_t* events;                // nullable
+    uint8_t* records;                // pairwise kernels: per-lane record scratch [grid * kThreads][MM * kSerStride]
     uint8_t* series;                 // nullable debug dump [total][series_stride]
     int32_t series_stride;
     unsigned long long* warp_iters;  // nullable debug counter: hot-loop iterations (2 steps each) summed over warps
@@ -494,14 +510,17 @@ __device__ __forceinline__ void lane_init(Lane<MM>& L, const LaunchArgs& A, cons
 // Results are identical in both modes.
 // kFast: every job's topology gives each gene at most one regulator (requires !kMixed && kAllSpecies).
 template <int MM, bool kMixed, bool kAllSpecies, bool kFast = false>
-__global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa_pairwise_kernel(const LaunchArgs A)
+__global__ void __launch_bounds__(kThreads, MM <= 3 ? CT_MINB3 : (MM == 4 ? CT_MINB4 : CT_MINB5)) ssa_pairwise_kernel(const LaunchArgs A)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    uint8_t* ser = smem + (size_t)threadIdx.x * (MM * kSerStride);
-    uint8_t* warp_ser = smem + (size_t)(warp * 32) * (MM * kSerStride);
-    float* z = reinterpret_cast<float*>(smem + (size_t)kThreads * (MM * kSerStride)) + warp * kSerStride;
+    // shared memory: per warp the reward scratch z[kSerStride] and the staging copy of ONE finished record
+    float* z = reinterpret_cast<float*>(smem) + warp * kSerStride;
+    uint8_t* stage = smem + (size_t)(kThreads / 32) * kSerStride * sizeof(float) + (size_t)warp * (MM * kSerStride);
+    // this lane's record and the first record of its warp, in the global scratch area
+    uint8_t* warp_ser = A.records + ((size_t)blockIdx.x * kThreads + (size_t)warp * 32) * (MM * kSerStride);
+    uint8_t* ser = warp_ser + (size_t)lane * (MM * kSerStride);
 
     static_assert(!kFast || (!kMixed && kAllSpecies), "kFast needs one full-size topology per warp");
     Lane<MM> L;
@@ -532,12 +551,17 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa
         if (idle) {
             // 1. reduce finished trajectories to (reward, lag), one lane at a time, whole warp helping
             unsigned fin = __ballot_sync(kFull, finished);
+            if (fin) __syncwarp();     // the finished lanes' record bytes are visible to the whole warp
             while (fin) {
                 const int src = __ffs(fin) - 1;
                 fin &= fin - 1;
                 float rw; int lg;
-                const uint8_t* sser = warp_ser + (size_t)src * (MM * kSerStride);
                 const int nsp_src = kMixed ? (int)(__shfl_sync(kFull, pres, src) >> 28) : nsp;
+                // stage the record in shared memory (L2 reads: another lane wrote it), then reduce it
+                const uint32_t* grec = reinterpret_cast<const uint32_t*>(warp_ser + (size_t)src * (MM * kSerStride));
+                for (int w = lane; w < nsp_src * (kSerStride / 4); w += 32) reinterpret_cast<uint32_t*>(stage)[w] = __ldcg(grec + w);
+                __syncwarp();
+                const uint8_t* sser = stage;
                 warp_reward(sser, z, nsp_src, A.n_dec, lane, rw, lg);
                 const uint32_t out = __shfl_sync(kFull, L.out, src);
                 if (A.series) {
@@ -545,6 +569,7 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? 4 : (MM == 4 ? 3 : 2)) ssa
                         for (int k = lane; k < A.n_dec; k += 32)
                             A.series[(size_t)out * A.series_stride + s * A.n_dec + k] = sser[s * kSerStride + k];
                 }
+                __syncwarp();          // everybody is done with the staged copy before the next one overwrites it
                 if (lane == src) {
                     A.reward[out] = rw;
                     if (A.lag) A.lag[out] = lg;

@@ -30,6 +30,9 @@ CASES = {
     "shared_heterodimer": (G4, "*ABC+R::ABiA_ABiB_CRaC_CCiA", 2500, 202, 800),
     "five_tf_ten_interactions": (G5, "*ABCDE+::AAiB_BBiC_CCiD_DDiE_EEiA_ABaA_BCaB_CDaC_DEaD_AEaE", 1000, 32, 800),
     "same_stream": (G4, "*ABC+R::AAiB_BBiC_CCiA", 1000, 9, 2000),
+    # a promoter with an activating AND an inhibiting dimer (km_act_rep, the A bookkeeping), a heterodimer
+    # with the regulator, and a heterodimer of two components on a third promoter
+    "mixed_promoter": (G4, "*ABC+R::AAaA_BRiA_ABiC", 2500, 202, 800),
 }
 
 
@@ -42,13 +45,17 @@ def run_case(name, n=None, n_threads=None):
 
 def main():
     out = {}
-    for name in CASES:
+    target = Path(__file__).with_name("dimer_oracle.npz")
+    only = sys.argv[1:]          # names to (re)record; the other cases are kept from the existing file
+    if only and target.exists():
+        out = dict(np.load(target))
+    for name in (only or CASES):
         r = run_case(name)
         out[name + "/reward"] = r["reward"]
         out[name + "/lag"] = r["lag"].astype(np.int16)
         out[name + "/n_events"] = r["n_events"].astype(np.uint32)
         print(name, r["reward"].mean(), r["n_events"].mean(), flush=True)
-    np.savez_compressed(Path(__file__).with_name("dimer_oracle.npz"), **out)
+    np.savez_compressed(target, **out)
 
 
 if __name__ == "__main__":

@@ -128,11 +128,12 @@ TOPOLOGIES = [
     "*ABC+R::ARaB_BBiC_CCiA",            # heterodimer with the regulator, one activation
     "*ABC+R::",                          # no interactions
     "*ABC+R::ABiA_ABiB_CRaC_CCiA",       # shared heterodimer on two promoters, two interactions on promoter A
+    "*ABC+R::AAaA_BRiA_ABiC",            # an activating AND an inhibiting dimer on promoter A (km_act_rep, the A bookkeeping)
 ]
-CASE_NAMES = ["homodimer_repressilator", "heterodimer_regulator", "no_interactions", "shared_heterodimer"]
+CASE_NAMES = ["homodimer_repressilator", "heterodimer_regulator", "no_interactions", "shared_heterodimer", "mixed_promoter"]
 
 
-@pytest.mark.parametrize("case", range(4))
+@pytest.mark.parametrize("case", range(5))
 def test_statistical_equivalence(eng, cfg, case):
     # the bar's 10^4 trajectories at the full grid for the oscillator; the others (1.7e6 events per
     # trajectory) at 2500 trajectories on a 800-point grid.  Checker side: recorded, seed 202.
@@ -176,8 +177,8 @@ def test_same_stream_trajectories_track_the_checker(eng, cfg):
 
 def test_launch_shape_independence_and_mixed_batches(eng):
     c = small_cfg(nt=320, decim=16)
-    counts = [700, 33, 64, 1]
-    bases = [0, 1000, 2000, 3000]
+    counts = [700, 33, 64, 1, 40]
+    bases = [0, 1000, 2000, 3000, 4000]
     mixed = gpu_run(eng, TOPOLOGIES, counts, c, seed=8, bases=bases)
     again = gpu_run(eng, TOPOLOGIES, counts, c, seed=8, bases=bases)
     off = np.concatenate(([0], np.cumsum(counts)))
@@ -194,25 +195,63 @@ def test_launch_shape_independence_and_mixed_batches(eng):
 
 
 def test_per_lane_programs_are_bit_identical(eng):
-    """Launches of many small jobs give every lane its own topology (ssa_dimers_mixed_kernel, schedule 2
-    or automatic); big jobs run one topology per warp (ssa_dimers_kernel, schedule 1).  Same bits."""
+    """Launches of many small jobs give every lane its own topology (ssa_dimers_mixed_kernel, schedule 2);
+    big jobs run one topology per warp (ssa_dimers_kernel, schedule 1); launches too small to fill the
+    device spread every trajectory over a sub-group of 8 or 4 lanes (ssa_dimers_coop_kernel, schedule 3,
+    and what schedule 0 picks here).  All follow the summation order of SPEC.md section 9: same bits."""
     g5 = DimersGrammar(components=list("ABCDE"), regulators=[], interactions=AI)
     cases = [
-        (GRAMMAR, TOPOLOGIES + ["*ABC+R::AAaA_BRiA_ABiC", "*ABC+R::CCaB"], [96, 40, 33, 64, 50, 7]),
+        (GRAMMAR, TOPOLOGIES + ["*ABC+R::CCaB"], [96, 40, 33, 64, 50, 7]),
         (g5, ["*ABCDE+::AAiB_BBiC_CCiD_DDiE_EEiA_ABaA_BCaB_CDaC_DEaD_AEaE", "*ABCDE+::AEaC", "*ABCDE+::"], [64, 30, 9]),
         # three interactions on promoter A: more than the per-lane kernel has slots -> it falls back, still equal
         (GRAMMAR, ["*ABC+R::AAaA_BBiA_CCiA_ABiB", "*ABC+R::AAiB"], [40, 24]),
     ]
     for grammar, states, counts in cases:
         outs = []
-        for schedule in (1, 2, 0):
+        for schedule in (1, 2, 3, 0):
             c = small_cfg(nt=400, decim=16)
             c.schedule = schedule
             outs.append(gpu_run(eng, states, counts, c, seed=23, bases=np.arange(len(states)) * 1000, grammar=grammar, series=True))
         for key in ("reward", "lag", "events", "series"):
-            assert np.array_equal(outs[0][key], outs[1][key]), (states[0], key)
-            assert np.array_equal(outs[0][key], outs[2][key]), (states[0], key)
+            for other in outs[1:]:
+                assert np.array_equal(outs[0][key], other[key]), (states[0], key)
         assert outs[0]["events"].sum() > 0
+    # three TFs and at most four dimers: sub-groups of 4 lanes (the other cases above use 8)
+    g3 = DimersGrammar(components=list("ABC"), regulators=[], interactions=AI)
+    states = ["*ABC+::AAiB_BBiC_CCiA", "*ABC+::ABaA_ABiB_BCaC_ACiC", "*ABC+::", "*ABC+::CCaC"]
+    outs = []
+    for schedule in (1, 2, 3):
+        c = small_cfg(nt=400, decim=16)
+        c.schedule = schedule
+        outs.append(gpu_run(eng, states, [70, 33, 5, 64], c, seed=29, bases=np.arange(4) * 1000, grammar=g3, series=True))
+    for key in ("reward", "lag", "events", "series"):
+        assert np.array_equal(outs[0][key], outs[1][key]) and np.array_equal(outs[0][key], outs[2][key]), key
+    assert outs[0]["events"].sum() > 0
+
+
+def test_cooperative_kernel_statistics_and_full_grid(eng, cfg):
+    """The cooperative kernel on its own, on the full grid: the oscillator's recorded checker
+    statistics (same bars as test_statistical_equivalence), and bit-equality with the one-lane kernels
+    over whole 2000-point trajectories (hundreds of thousands of events each)."""
+    state = TOPOLOGIES[0]
+    n = 10_000
+    coop = _capi.default_config(); coop.schedule = 3
+    g = gpu_run(eng, [state], n, coop, seed=101)
+    o = recorded(CASE_NAMES[0])
+    se = np.sqrt(g["reward"].var(ddof=1) / n + o["reward"].var(ddof=1) / n)
+    assert abs(g["reward"].mean() - o["reward"].mean()) < 3.0 * se
+    assert stats.ks_2samp(g["lag"], o["lag"]).pvalue > 0.01
+    se_ev = np.sqrt(g["events"].var(ddof=1) / n + o["n_events"].astype(float).var(ddof=1) / n)
+    assert abs(g["events"].mean() - o["n_events"].mean()) < 3.5 * se_ev
+    uni = _capi.default_config(); uni.schedule = 1
+    u = gpu_run(eng, [state], n, uni, seed=101)
+    for key in ("reward", "lag", "events"):
+        assert np.array_equal(g[key], u[key]), key
+    # a single small call (the reference's sequential get_reward): one launch of 16 trajectories
+    few = gpu_run(eng, [TOPOLOGIES[3]], 16, coop, seed=5)
+    ref = gpu_run(eng, [TOPOLOGIES[3]], 16, uni, seed=5)
+    for key in ("reward", "lag", "events"):
+        assert np.array_equal(few[key], ref[key]), key
 
 
 def test_one_model_per_launch(eng):

@@ -172,6 +172,27 @@ def test_recorded_dimer_results_are_what_the_checker_computes():
         assert np.array_equal(r["n_events"], gold[name + "/n_events"][:12]), name
 
 
+def test_recorded_sweep_results_are_what_the_checker_computes():
+    """tests/golden/sweep_oracle.npz (the randomised GPU parity sweep) against a fresh run of a slice."""
+    import importlib.util
+    from pathlib import Path
+
+    here = Path(__file__).parent / "golden"
+    spec = importlib.util.spec_from_file_location("make_sweep_oracle", here / "make_sweep_oracle.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    gold = np.load(here / "sweep_oracle.npz")
+    states = mod.states()
+    assert [str(s) for s in gold["states"]] == states and len(states) == 200
+    assert sum(s.startswith("*ABCD::") for s in states) == 100
+    for i in (0, 57, 100, 133, 199):
+        r = mod.run_state(i, states[i], n=mod.N_RAW, n_threads=4)
+        assert np.array_equal(r["reward"], gold["raw_reward"][i]), states[i]
+        assert np.array_equal(r["lag"], gold["raw_lag"][i]), states[i]
+        assert np.array_equal(r["n_events"], gold["raw_events"][i]), states[i]
+    assert (gold["reward_var"] > 0).all() and (gold["events_mean"] > 1e3).all()
+
+
 def test_unregulated_gene_matches_birth_death_theory():
     """An external anchor for the unpinned model: one unregulated gene is the textbook two-stage
     birth-death process -- stationary means R = km/gm, P = km kp/(gm gp), and 2 km (1 + kp/gm) events
@@ -247,18 +268,18 @@ def test_promoter_binding_matches_exact_telegraph_moments():
     prm = [k_on, k_off1, k_off2, km0, km_a, km_r, km_ar, 0.0, gm, 0.0]
     a, b = 2 * k_on, k_off1
     # A inhibits B
-    r, tot = _telegraph_run(2, [], [(0, 1)], prm, 40_000, seed=71)
+    r, tot = _telegraph_run(2, [], [(0, 1)], prm, 25_000, seed=71)
     mean, var = switching_moments([[-a, a], [b, -b]], [km0, km_r], gm)
     _check_moments(r[tot[:, 0] == 1, 1], mean, var, "inhibitor")
     # the unregulated gene A is a plain birth-death process: Poisson with mean km0 / gm
     assert abs(r[:, 0].mean() - km0 / gm) < 4 * np.sqrt(km0 / gm / len(r))
     assert abs(r[:, 0].var(ddof=1) / r[:, 0].mean() - 1.0) < 0.05
     # A activates B
-    r, tot = _telegraph_run(2, [(0, 1)], [], prm, 40_000, seed=72)
+    r, tot = _telegraph_run(2, [(0, 1)], [], prm, 25_000, seed=72)
     mean, var = switching_moments([[-a, a], [b, -b]], [km0, km_a], gm)
     _check_moments(r[tot[:, 0] == 1, 1], mean, var, "activator")
     # A activates C, B inhibits C, one molecule each: promoter states (bA, bB) = 00, 10, 01, 11
-    r, tot = _telegraph_run(3, [(0, 2)], [(1, 2)], prm, 120_000, seed=73)
+    r, tot = _telegraph_run(3, [(0, 2)], [(1, 2)], prm, 80_000, seed=73)
     Q = np.zeros((4, 4))
     Q[0, 1] = 2 * k_on; Q[0, 2] = 2 * k_on          # first molecule: two free sites
     Q[1, 3] = k_on; Q[2, 3] = k_on                  # second molecule: one free site
