@@ -3,6 +3,7 @@
 // compute entry point fails with CT_ERR_NO_DEVICE / CT_ERR_CUDA.
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <nvtx3/nvToolsExt.h>      // header-only; ranges cost nothing unless a profiler is attached
 
 #include <cstdarg>
 #include <cstdio>
@@ -41,6 +42,12 @@ int fail(int code, const char* fmt, ...)
 struct KernelInfo {
     int blocks_per_sm = 0;
     size_t smem = 0;
+};
+
+// NVTX range for the duration of a C-ABI call (shows up on the timeline of nsys / ncu --nvtx)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
 };
 
 // Stream-ordered scratch of one call: everything handed out is released (cudaFreeAsync on the same
@@ -351,6 +358,7 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
                       const float* d_params, float* d_reward, int32_t* d_lag, uint32_t* d_events, uint8_t* d_series,
                       int32_t series_stride)
 {
+    NvtxRange nvtx_range("ct_launch_rewards");
     if (!eng) return fail(CT_ERR_INVALID, "engine is NULL");
     if (n_jobs < 0 || (n_jobs && (!handles || !n_traj || !traj_base))) return fail(CT_ERR_INVALID, "bad job arrays");
     int rc = validate_cfg(cfg);
@@ -582,6 +590,7 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
 int ct_reduce_jobs(ct_engine* eng, const uint32_t* n_traj, int32_t n_jobs, void* stream_, const float* d_reward,
                    const uint32_t* d_events, double* d_job_mean, uint64_t* d_job_events)
 {
+    NvtxRange nvtx_range("ct_reduce_jobs");
     if (!eng) return fail(CT_ERR_INVALID, "engine is NULL");
     if (n_jobs < 0 || (n_jobs && (!n_traj || !d_reward || !d_job_mean))) return fail(CT_ERR_INVALID, "bad arguments");
     if (n_jobs == 0) return CT_OK;
@@ -608,6 +617,7 @@ int ct_rewards_host(ct_engine* eng, const uint64_t* handles, const uint32_t* n_t
                     const float* job_cost, int32_t n_jobs, const ct_sim_config* cfg, uint64_t seed, const float* h_params,
                     double* h_job_mean, uint64_t* h_job_events, float* h_reward, int32_t* h_lag)
 {
+    NvtxRange nvtx_range("ct_rewards_host");
     if (!eng) return fail(CT_ERR_INVALID, "engine is NULL");
     if (n_jobs < 0 || (n_jobs && (!handles || !n_traj || !traj_base))) return fail(CT_ERR_INVALID, "bad job arrays");
     if (n_jobs == 0) return CT_OK;
@@ -701,6 +711,7 @@ int ct_rewards_submit(ct_engine* eng, const uint64_t* handles, const uint32_t* n
                       const float* job_cost, int32_t n_jobs, const ct_sim_config* cfg, uint64_t seed, const float* h_params,
                       int64_t* ticket)
 {
+    NvtxRange nvtx_range("ct_rewards_submit");
     if (!eng || !ticket) return fail(CT_ERR_INVALID, "engine or ticket is NULL");
     if (n_jobs < 1 || !handles || !n_traj || !traj_base) return fail(CT_ERR_INVALID, "bad job arrays");
     CT_CUDA(cudaSetDevice(eng->device));
@@ -725,6 +736,7 @@ int ct_rewards_submit(ct_engine* eng, const uint64_t* handles, const uint32_t* n
 int ct_rewards_wait(ct_engine* eng, int64_t ticket, double* h_job_mean, uint64_t* h_job_events, float* h_reward,
                     int32_t* h_lag)
 {
+    NvtxRange nvtx_range("ct_rewards_wait");
     if (!eng) return fail(CT_ERR_INVALID, "engine is NULL");
     auto it = eng->tickets.find(ticket);
     if (it == eng->tickets.end()) return fail(CT_ERR_INVALID, "unknown ticket %lld", (long long)ticket);

@@ -26,6 +26,8 @@
 #include <unordered_map>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/circuitree_b200.h"
 
 namespace {
@@ -41,6 +43,11 @@ int tfail(int code, const char* fmt, ...)
 }
 
 typedef unsigned __int128 u128;
+
+struct NvtxRange {     // host-side phases of the scheduler on the profiler timeline
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 // ---- numpy's PCG64 (XSL-RR 128/64) and the two bounded-integer algorithms the reference uses ----
 struct Pcg64 {
@@ -528,6 +535,7 @@ int ct_tree_rng_draw(ct_tree* t, int32_t kind, int64_t n, int64_t* out)
  * selected in *n_done (fewer than k only when the tree is exhausted). */
 int ct_tree_select(ct_tree* t, int32_t k, uint64_t* sim_keys, uint64_t* sim_handles, int32_t* n_done)
 {
+    NvtxRange nvtx_range("ct_tree_select");
     if (!t || k < 0 || !n_done) return tfail(CT_ERR_INVALID, "bad arguments");
     *n_done = 0;
     std::vector<int> path;
@@ -550,6 +558,7 @@ int ct_tree_select(ct_tree* t, int32_t k, uint64_t* sim_keys, uint64_t* sim_hand
 /* Back-propagate rewards for the k oldest pending selections (FIFO). */
 int ct_tree_backprop(ct_tree* t, int32_t k, const double* rewards)
 {
+    NvtxRange nvtx_range("ct_tree_backprop");
     if (!t || k < 0 || (k && !rewards)) return tfail(CT_ERR_INVALID, "bad arguments");
     if ((size_t)k > t->pending.size() - t->pending_head) return tfail(CT_ERR_INVALID, "more rewards than pending selections");
     for (int x = 0; x < k; ++x) {
@@ -651,6 +660,7 @@ int ct_tree_key_to_handle(ct_tree* t, uint64_t key, uint64_t* handle)
 /* Exhaustive expansion from the root in the reference's stack order (circuitree.py:565-586). */
 int ct_tree_grow(ct_tree* t)
 {
+    NvtxRange nvtx_range("ct_tree_grow");
     if (!t) return tfail(CT_ERR_INVALID, "NULL tree");
     std::vector<std::pair<int, int>> stack;
     std::vector<int> acts;
@@ -690,6 +700,7 @@ constexpr int64_t kPackHeader = 5;
 
 int ct_tree_pack_deltas(ct_tree* t, int32_t max_depth, int64_t* buf, int64_t cap, int64_t* n_words)
 {
+    NvtxRange nvtx_range("ct_tree_pack_deltas");
     if (!t || !n_words) return tfail(CT_ERR_INVALID, "NULL argument");
     if (t->track_exhaustion) t->settle_exhausted();
     auto wanted = [&](uint64_t key) { return max_depth < 0 || t->depth_of(key) <= max_depth; };
@@ -731,6 +742,7 @@ int ct_tree_pack_deltas(ct_tree* t, int32_t max_depth, int64_t* buf, int64_t cap
  * would hold had it executed every path.  *tree_exhausted (nullable) is set when the root is flagged. */
 int ct_tree_merge_packed(ct_tree* t, const int64_t* buf, int64_t n_words, int32_t* tree_exhausted)
 {
+    NvtxRange nvtx_range("ct_tree_merge_packed");
     if (!t || !buf) return tfail(CT_ERR_INVALID, "NULL argument");
     if (n_words < kPackHeader || buf[0] != kPackMagic) return tfail(CT_ERR_INVALID, "not a delta buffer");
     const int64_t nn = buf[1], ne = buf[2], nx = buf[3];

@@ -25,15 +25,21 @@
 #define CT_UNROLL_H 1         // 1: the two steps of a Philox block are unrolled into one basic block
 #endif
 // Resident CTAs per SM the compiler has to make room for (registers per thread <= 65536 / (128 * n)),
-// for M = 3, 4, 5.  Measured on B200 (profiles/r02_*): see there for the choice.
+// for M = 3, 4, 5.  With the record out of shared memory registers alone set the residency, and the
+// compiler fits the hot variants into 96 (M = 3) / 128 (M = 4, 5) registers without spilling -- but
+// more resident warps made every variant SLOWER on B200 (profiles/r02_occupancy_variants.txt, 2^21
+// repressilator trajectories: 4 CTAs 1.57e11 steps/s, 5 CTAs 1.43e11, 6 CTAs 1.22e11; five-component
+// MCTS batches: 2 CTAs 3.1e10, 3 CTAs 3.0e10, 4 CTAs 2.5e10): the loop is not short of eligible warps
+// (ncu: 1.75 eligible-but-not-selected warps per issue), it is bound by dispatch and pipe conflicts that
+// tighter register allocation makes worse.  Hence the round-1 residency.
 #ifndef CT_MINB3
-#define CT_MINB3 5
+#define CT_MINB3 4
 #endif
 #ifndef CT_MINB4
-#define CT_MINB4 4
+#define CT_MINB4 3
 #endif
 #ifndef CT_MINB5
-#define CT_MINB5 4
+#define CT_MINB5 2
 #endif
 
 namespace ct {
