@@ -94,9 +94,14 @@ inline int params_per_trajectory(const uint64_t* handles, int n_jobs)
 }  // namespace
 
 namespace {
-// automatic schedule: dimer launches of up to this many times the resident one-lane-per-trajectory
-// lanes run on the cooperative kernel (measured switch-over)
-constexpr int kCoopAutoFactor = 2;
+// automatic schedule: dimer launches of up to this many times the resident one-lane-per-trajectory lanes
+// (75,776 on B200) run on the cooperative kernel.  Measured (profiles/r02_dimer_schedules_*.txt): one topology,
+// 2^16 trajectories: cooperative 2.5 s, one topology per warp 6.4 s; 2^20: one topology per warp 7 s (it
+// refills its lanes from the same job and saturates at 4e10 steps/s, the cooperative kernel at ~1e10);
+// batches of random five-TF topologies x 32 trajectories: 1024 leaves 36 s vs 112 s per-lane programs,
+// 4096 leaves 31 s vs 86 s -- such batches last as long as their longest trajectory.
+constexpr int kCoopAutoFactorOne = 2;
+constexpr int kCoopAutoFactorMany = 8;
 
 struct Ticket {                      // one asynchronous reward batch in flight
     cudaStream_t stream = nullptr;
@@ -471,7 +476,8 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
     // get_reward calls -- last as long as their longest trajectory: spread each trajectory over a sub-group
     // of lanes instead (ssa_dimers_coop.cuh; identical results).
     bool coop = dimers && lane_progs_ok && cfg->schedule == 3;
-    if (dimers && lane_progs_ok && cfg->schedule == 0) coop = total <= (uint64_t)kCoopAutoFactor * resident;
+    if (dimers && lane_progs_ok && cfg->schedule == 0)
+        coop = total <= (uint64_t)(n_jobs > 1 ? kCoopAutoFactorMany : kCoopAutoFactorOne) * resident;
     if (coop) mixed = true;                        // (launch positions, not per-job tiles)
     if (mixed) A.n_tiles = (uint32_t)((total + ct::kTile - 1) / ct::kTile);   // tiles over launch positions
 

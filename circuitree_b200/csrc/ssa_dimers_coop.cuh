@@ -82,6 +82,8 @@ ssa_dimers_coop_kernel(const LaunchArgs A, const DimerLaneProg* __restrict__ lpr
     uint8_t* rec = warp_rec + (size_t)sub * rec_bytes + (size_t)(l < kTf ? l : 0) * kSerStride;   // my TF's row of the record
     const bool tf_role = l < kTf;
     const int q = l - kTf;                                                          // dimer block of a dimer lane
+    float lf;       // my position in the sub-group as a float the compiler cannot trace back to the integer
+    asm volatile("cvt.rn.f32.s32 %0, %1;" : "=f"(lf) : "r"(l));
 
     // The lane's program, fixed while a trajectory runs: operand addresses and rates of its block.
     //   TF lane:    op = {N, A, R, P, D(slot 0), D(slot 1), B0, B1};
@@ -228,10 +230,11 @@ ssa_dimers_coop_kernel(const LaunchArgs A, const DimerLaneProg* __restrict__ lpr
         const Philox4 x = philox4x32_10_rk(ctr + (uint32_t)l, 1u, traj_lo, traj_hi, A.rk);
         ctr += G;
 #pragma unroll 1
-        for (int j = 0; j < 2 * G; ++j) {
-            const uint32_t wa = (j & 1) ? x.w[2] : x.w[0], wb = (j & 1) ? x.w[3] : x.w[1];
-            const uint32_t w_tau = __shfl_sync(kFull, wa, base + (j >> 1));
-            const uint32_t w_sel = __shfl_sync(kFull, wb, base + (j >> 1));
+        for (int pr = 0; pr < G; ++pr) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {       // (two steps per block, unrolled: no word selects in the loop)
+            const uint32_t w_tau = __shfl_sync(kFull, h ? x.w[2] : x.w[0], pr, G);
+            const uint32_t w_sel = __shfl_sync(kFull, h ? x.w[3] : x.w[1], pr, G);
 
             // ---- my block's running sum (starts at zero: SPEC.md section 9) ----
             float c[8];
@@ -263,11 +266,13 @@ ssa_dimers_coop_kernel(const LaunchArgs A, const DimerLaneProg* __restrict__ lpr
                 }
             }
             // ---- block offsets: totals added up in block order; a0 is the last offset ----
+            // (my own offset is the same chain cut off at my block: the mask is 1 for blocks before mine, else 0,
+            // and comes from the FMA pipe -- compares and selects run at half its rate and are the scarce resource here)
             float o = 0.0f, my_lo = 0.0f;
 #pragma unroll
             for (int b = 0; b < G; ++b) {
-                const float gb = __shfl_sync(kFull, c[7], base + b);
-                if (b == l) my_lo = o;
+                const float gb = __shfl_sync(kFull, c[7], b, G);
+                my_lo = fmaf(__saturatef(lf - (float)b), gb, my_lo);
                 o += gb;
             }
             const float a0 = o;
@@ -296,15 +301,20 @@ ssa_dimers_coop_kernel(const LaunchArgs A, const DimerLaneProg* __restrict__ lpr
             // ---- the lane whose block holds the target fires its entry ----
             const float t = alive ? u01(w_sel) * a0 : 3.0e38f;
             const float tl = t - my_lo;
-            int r = 0;
+            // first entry with tl < c_r = number of entries with c_i <= tl; [c_i > tl] = saturate((c_i - tl) 2^80) is
+            // exact for sums that are zero or above 2^-56 (the scaling is a power of two, the sign that of the exact difference)
+            constexpr float kBig = 1208925819614629174706176.0f;      // 2^80
+            const float tb = -tl * kBig;
+            float above = 0.0f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) r += (c[i] <= tl) ? 1 : 0;      // first entry with tl < c_r
+            for (int i = 0; i < 8; ++i) above += __saturatef(fmaf(c[i], kBig, tb));
+            const int r = 8 - (int)above;
             if (my_lo <= t && t < my_hi && r < 8) {
                 const uint4 e = *reinterpret_cast<const uint4*>(tab + r);
-                float* p0 = Xs + (e.x & 0xffu);
-                float* p1 = Xs + ((e.x >> 8) & 0xffu);
-                float* p2 = Xs + ((e.x >> 16) & 0xffu);
-                float* p3 = Xs + (e.x >> 24);
+                float* p0 = Xs + __byte_perm(e.x, 0u, 0x4440);
+                float* p1 = Xs + __byte_perm(e.x, 0u, 0x4441);
+                float* p2 = Xs + __byte_perm(e.x, 0u, 0x4442);
+                float* p3 = Xs + __byte_perm(e.x, 0u, 0x4443);
                 const float2 d01 = __half22float2(*reinterpret_cast<const __half2*>(&e.y));
                 const float2 d23 = __half22float2(*reinterpret_cast<const __half2*>(&e.z));
                 const float v0 = *p0, v1 = *p1, v2 = *p2, v3 = *p3;     // distinct slots
@@ -321,6 +331,7 @@ ssa_dimers_coop_kernel(const LaunchArgs A, const DimerLaneProg* __restrict__ lpr
                 t_rem = 0.0f; blk = 0.0f;
             }
             __syncwarp();       // the fired updates are visible to the whole sub-group before the next step reads
+        }
         }
     }
     if (A.warp_iters && lane == 0) atomicAdd(A.warp_iters, (unsigned long long)n_iters);

@@ -16,6 +16,7 @@ ap.add_argument("--sizes", default="8,10,12,14,16")
 ap.add_argument("--leaves", default="256,1024")
 ap.add_argument("--traj", type=int, default=32)
 ap.add_argument("--schedules", default="1,2,3")
+ap.add_argument("--wide-sizes", default="", help="launch sizes (log2) for the five-TF topology (default: --sizes)")
 args = ap.parse_args()
 AI = ["activates", "inhibits"]
 eng = _capi.Engine(0)
@@ -46,7 +47,8 @@ one = [(G3, "*ABC+::AAiB_BBiC_CCiA"), (G5, "*ABC+DE::ADiB_BEiC_CCiA_ABaA_DEaB_BC
 run([handle(*one[0])], [64], 1)   # warm-up
 for g, s in one:
     h = handle(g, s)
-    for k in [int(x) for x in args.sizes.split(",")]:
+    sizes = args.wide_sizes if (g is G5 and args.wide_sizes) else args.sizes
+    for k in [int(x) for x in sizes.split(",")]:
         ref = None
         for sc in scheds:
             dt, ev, util, out = run([h], [1 << k], sc)

@@ -1,5 +1,6 @@
 """One launch of the dimer kernel (homodimer repressilator, SPEC.md section 9) for ncu / timing.
-usage: prof_dimers.py [log2 n] [nt] [reps] [big]   (big = five TFs, ten interactions, ten dimers)"""
+usage: prof_dimers.py [log2 n] [nt] [reps] [big|small] [schedule]
+(big = five TFs, ten interactions, ten dimers; schedule 1 one topology per warp, 2 per lane, 3 cooperative sub-groups)"""
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
@@ -12,6 +13,7 @@ reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 eng = _capi.Engine(0)
 cfg = _capi.default_config()
 cfg.nt = nt
+cfg.schedule = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 if len(sys.argv) > 4 and sys.argv[4] == "big":
     # *ABCDE+::AAiB_BBiC_CCiD_DDiE_EEiA_ABaA_BCaB_CDaC_DEaD_AEaE
     h = _capi.compile_topology(5, [(0, 1, 0), (1, 2, 1), (2, 3, 2), (3, 4, 3), (0, 4, 4)],
