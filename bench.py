@@ -412,7 +412,7 @@ def main() -> None:
         e0, s0 = tree3.reward_engine.total_events, tree3.reward_engine.total_issue_slots
         barrier()
         t0 = time.perf_counter()
-        tree3.search_mcts(args.mcts3_iters, batch_size=args.mcts3_batch, pipeline_depth=2)
+        tree3.search_mcts(args.mcts3_iters, batch_size=args.mcts3_batch, pipeline_depth=args.mcts_depth)
         barrier()
         secs = time.perf_counter() - t0
         (secs,), (ev, slots) = over_ranks([secs], [tree3.reward_engine.total_events - e0, tree3.reward_engine.total_issue_slots - s0])
@@ -420,7 +420,7 @@ def main() -> None:
                          "reaction_steps_per_s": ev / secs, "roofline_frac": slots / secs / world / 1e12 / peak,
                          "config": {"workload": f"SimpleNetworkGrammar ABC (activates/inhibits) oscillation-reward MCTS, "
                                                 f"{args.mcts3_iters} iterations per GPU (independent trees), {args.mcts_traj} SSA "
-                                                f"trajectories per rollout, {args.mcts3_batch} leaves per launch, 2 launches in flight",
+                                                f"trajectories per rollout, {args.mcts3_batch} leaves per launch, {args.mcts_depth} launches in flight",
                                     "quality_rank0": tree_quality(tree3, "ABC::")}}
         del tree3
 
@@ -505,15 +505,15 @@ def main() -> None:
         dtree = OscillationTree(grammar=dg, root="ABC+DE::", seed=rank, n_exhausted=np.inf, trajectories_per_reward=args.mcts_traj,
                                 device=local_rank)
         dtree.search_mcts_batched(64, 64)                                        # warm-up
-        e0 = dtree.reward_engine.total_events
+        e0, s0 = dtree.reward_engine.total_events, dtree.reward_engine.total_issue_slots
         barrier()
         t0 = time.perf_counter()
         dtree.search_mcts_batched(args.dimer_search_rollouts, 1024, pipeline_depth=4)
         barrier()
         secs = time.perf_counter() - t0
-        (secs,), (ev,) = over_ranks([secs], [dtree.reward_engine.total_events - e0])
+        (secs,), (ev, slots) = over_ranks([secs], [dtree.reward_engine.total_events - e0, dtree.reward_engine.total_issue_slots - s0])
         line["dimer_search"] = {"metric": "mcts_rollouts_per_s", "value": world * args.dimer_search_rollouts / secs, "unit": "rollouts/s",
-                                "reaction_steps_per_s": ev / secs,
+                                "reaction_steps_per_s": ev / secs, "roofline_frac": slots / secs / world / 1e12 / peak,
                                 "config": {"workload": f"DimersGrammar ABC+DE (five TFs) oscillation search, {args.dimer_search_rollouts} "
                                                        f"rollouts per GPU (independent trees), {args.mcts_traj} trajectories per rollout, "
                                                        "1024 leaves per launch, 4 launches in flight; the full 10^5-rollout run is "
@@ -556,7 +556,7 @@ def main() -> None:
                                               f"({ev} events in {dt:.1f} s); CPU restatement of SPEC.md (plain direct method, every "
                                               "propensity re-evaluated each step, gcc -O2), upstream has no SSA"}
             if "mcts3" in line:
-                line["mcts3"]["cpu_baseline"] = cpu_mcts_sample(150, args.mcts_traj, threads)
+                line["mcts3"]["cpu_baseline"] = cpu_mcts_sample(40, args.mcts_traj, threads)
         print(json.dumps(line))
     if world > 1:
         barrier()

@@ -46,10 +46,11 @@ class RewardEngine:
         self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         self._engine: Optional[_capi.Engine] = None
         self._handles: dict[Hashable, int] = {}
+        self._dimer_shape: dict[int, tuple[int, int]] = {}    # dimer handle -> (reactions, TFs)
         self.next_traj = 0           # trajectory ids handed out so far (fresh Philox streams per call)
         self.total_events = 0
         self.total_trajectories = 0
-        self.total_issue_slots = 0.0  # sum over pairwise jobs of events x I_step(R, M) (SPEC.md section 8): roofline numerator
+        self.total_issue_slots = 0.0  # sum over jobs of events x I_step (SPEC.md section 8): roofline numerator
         self.cost: dict[int, float] = {}   # topology handle -> events per trajectory observed so far
         self.share = 1               # asynchronous batches kept in flight: each gets 1/share of the CTA slots
 
@@ -69,6 +70,10 @@ class RewardEngine:
             else:
                 comps, regs, act, inh = parsed
                 h = _capi.compile_topology(len(comps) + len(regs), act, inh, k=3)
+                # reactions of the dimer model (SPEC.md section 9): 4 per TF, 2 per interaction, 2 per distinct dimer
+                rows = np.concatenate([np.asarray(act).reshape(-1, 3), np.asarray(inh).reshape(-1, 3)])
+                n_tf = len(comps) + len(regs)
+                self._dimer_shape[h] = (4 * n_tf + 2 * len(rows) + 2 * len({(int(a), int(b)) for a, b, _ in rows}), n_tf)
             self._handles[state] = h
         return h
 
@@ -98,9 +103,16 @@ class RewardEngine:
 
 
     def _count_issue_slots(self, handles: np.ndarray, job_events: np.ndarray) -> None:
-        if len(handles) and not _capi.is_dimer_handle(int(handles[0])):
+        if not len(handles):
+            return
+        if not _capi.is_dimer_handle(int(handles[0])):
             r, m = pairwise_shape(handles)
             self.total_issue_slots += float((job_events.astype(np.float64) * _capi_defaults.i_step(r, m)).sum())
+        else:
+            shape = np.array([self._dimer_shape.get(int(h), (0, 0)) for h in handles], dtype=np.float64)
+            known = shape[:, 0] > 0
+            self.total_issue_slots += float((job_events.astype(np.float64)[known] *
+                                             _capi_defaults.i_step_dimers(shape[known, 0], shape[known, 1])).sum())
 
     # -- asynchronous batches of leaves (pipelined MCTS) ---------------------------------------------------
     def submit_leaves(self, handles: np.ndarray, trajectories_per_leaf: int) -> dict:

@@ -29,7 +29,7 @@ root = f"{args.components}+{args.regulators}::"
 tree = OscillationTree(grammar=grammar, root=root, seed=args.seed, n_exhausted=np.inf, trajectories_per_reward=args.traj)
 tree.search_mcts_batched(min(256, args.rollouts), 256)                      # warm-up (engine, handles)
 eng = tree.reward_engine
-ev0, tr0, v0 = eng.total_events, eng.total_trajectories, tree.graph.nodes[root]["visits"]
+ev0, tr0, v0, sl0 = eng.total_events, eng.total_trajectories, tree.graph.nodes[root]["visits"], eng.total_issue_slots
 t0 = time.perf_counter()
 
 
@@ -50,6 +50,7 @@ print(json.dumps({
               f"{args.traj} trajectories per rollout, {args.depth} batches in flight",
     "seconds": round(dt, 2), "rollouts_per_s": args.rollouts / dt,
     "reaction_steps_per_s": (eng.total_events - ev0) / dt, "trajectories": eng.total_trajectories - tr0,
+    "issue_roofline_frac": (eng.total_issue_slots - sl0) / dt / (eng.engine.n_sm * 128 * 1.965e9),   # SPEC.md section 8 dimer I_step
     "events_per_trajectory": (eng.total_events - ev0) / max(1, eng.total_trajectories - tr0),
     "tree_nodes": tree.graph.number_of_nodes(), "root_visits": tree.graph.nodes[root]["visits"] - v0,
     "distinct_topologies_simulated": len(eng._handles),
