@@ -215,8 +215,8 @@ def main() -> None:
     ap.add_argument("--mcts3-batch", type=int, default=1024)
     ap.add_argument("--dimer-log2-traj", type=int, default=20, help="trajectories of the dimer-model leg = 2^T")
     ap.add_argument("--dimer-search-rollouts", type=int, default=4096)
-    ap.add_argument("--landscape-topologies", type=int, default=512)
-    ap.add_argument("--landscape-param-sets", type=int, default=256)
+    ap.add_argument("--landscape-topologies", type=int, default=3325, help="config 5 leg: sample size (3325 = every 3-component terminal)")
+    ap.add_argument("--landscape-param-sets", type=int, default=512)
     args = ap.parse_args()
 
     if args.impl == "reference":
