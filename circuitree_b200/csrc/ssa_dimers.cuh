@@ -371,6 +371,7 @@ __global__ void __launch_bounds__(kDimThreads, 10) ssa_dimers_kernel(const Launc
                     if (--dcount == 0) {
                         dcount = A.decim;
 #pragma unroll 1
+                        CT_CHECK(kd >= 0 && kd < kSerStride);
                         for (int s = 0; s < n_tf; ++s) {
                             ser[s * kSerStride + kd] = (uint8_t)compand_block(X[(kSlotBlk + s) * 32]);
                             X[(kSlotBlk + s) * 32] = 0.0f;
@@ -413,7 +414,9 @@ __global__ void __launch_bounds__(kDimThreads, 10) ssa_dimers_kernel(const Launc
                 hi = lt ? mid : hi;
                 lo = (open && !lt) ? mid + 1 : lo;
             }
+            CT_CHECK(lo >= 0 && lo <= n_entries && n_entries <= kMaxEntries && (int)(cp - cum) == n_entries * 32);
             const uint32_t sw = G->stoich[(lo < blk_end) ? lo : n_entries];
+            CT_CHECK((sw & 63u) < kSlots && ((sw >> 8) & 63u) < kSlots && ((sw >> 16) & 63u) < kSlots && ((sw >> 24) & 63u) < kSlots);
             // the four fields name distinct slots: load all, then store all
             float* f0 = X + (sw & 63u) * 32;
             float* f1 = X + ((sw >> 8) & 63u) * 32;
@@ -696,6 +699,7 @@ __global__ void __launch_bounds__(kDimThreads, 8) ssa_dimers_mixed_kernel(const 
                     if (--dcount == 0) {
                         dcount = A.decim;
 #pragma unroll 1
+                        CT_CHECK(kd >= 0 && kd < kSerStride);
                         for (int s = 0; s < n_tf; ++s) {
                             ser[s * kSerStride + kd] = (uint8_t)compand_block(X[(kSlotBlk + s) * 32]);
                             X[(kSlotBlk + s) * 32] = 0.0f;
@@ -762,6 +766,8 @@ __global__ void __launch_bounds__(kDimThreads, 8) ssa_dimers_mixed_kernel(const 
                 if (da != db) { s1 = kSlotP + db;   d1 = sg; }
                 s2 = kSlotD + d;    d2 = -sg;
             }
+            CT_CHECK(s0 >= 0 && s0 < kSlots && s1 >= 0 && s1 < kSlots && s2 >= 0 && s2 < kSlots && s3 >= 0 && s3 < kSlots);
+            CT_CHECK(lo >= 0 && lo <= n_entries && (int)(cp - cum) == n_entries * 32);
             float* f0 = X + s0 * 32;
             float* f1 = X + s1 * 32;
             float* f2 = X + s2 * 32;

@@ -289,6 +289,7 @@ ssa_dimers_coop_kernel(const LaunchArgs A, const DimerLaneProg* __restrict__ lpr
                     k += 1;
                     if (--dcount == 0) {
                         dcount = A.decim;
+                        CT_CHECK(kd >= 0 && kd < kSerStride && n_tf <= ser_species);
                         if (l < n_tf) rec[kd] = (uint8_t)compand_block(blk);
                         blk = 0.0f;
                         kd += 1;
@@ -315,6 +316,8 @@ ssa_dimers_coop_kernel(const LaunchArgs A, const DimerLaneProg* __restrict__ lpr
                 float* p1 = Xs + __byte_perm(e.x, 0u, 0x4441);
                 float* p2 = Xs + __byte_perm(e.x, 0u, 0x4442);
                 float* p3 = Xs + __byte_perm(e.x, 0u, 0x4443);
+                CT_CHECK(r >= 0 && r < 8 && (e.x & 0xffu) < kSlots && ((e.x >> 8) & 0xffu) < kSlots &&
+                         ((e.x >> 16) & 0xffu) < kSlots && (e.x >> 24) < kSlots);
                 const float2 d01 = __half22float2(*reinterpret_cast<const __half2*>(&e.y));
                 const float2 d23 = __half22float2(*reinterpret_cast<const __half2*>(&e.z));
                 const float v0 = *p0, v1 = *p1, v2 = *p2, v3 = *p3;     // distinct slots

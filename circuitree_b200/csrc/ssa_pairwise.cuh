@@ -42,6 +42,15 @@
 #define CT_MINB5 2
 #endif
 
+// -DCT_DEBUG_BOUNDS: every computed shared/global index of the hot loops is range-checked and the
+// kernel traps on a violation (compute-sanitizer is closed on this pool; scripts/sanitize_smoke.py
+// runs every kernel family on such a build, profiles/r02_bounds_checked_smoke.txt).
+#ifdef CT_DEBUG_BOUNDS
+#define CT_CHECK(cond) do { if (!(cond)) __trap(); } while (0)
+#else
+#define CT_CHECK(cond) do { } while (0)
+#endif
+
 namespace ct {
 
 constexpr int kThreads = 128;        // 4 warps per CTA
@@ -313,6 +322,7 @@ __device__ __forceinline__ void ssa_step(Lane<MM>& L, bool& active, bool& finish
                 L.dcount = decim;
 #pragma unroll
                 for (int j = 0; j < MM; ++j) {
+                    CT_CHECK(L.kd >= 0 && L.kd < kSerStride);
                     if (j < nsp) ser[j * kSerStride + L.kd] = (uint8_t)compand_block(L.blk[j]);
                     L.blk[j] = 0.0f;
                 }
@@ -570,6 +580,7 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? CT_MINB3 : (MM == 4 ? CT_M
                 const uint8_t* sser = stage;
                 warp_reward(sser, z, nsp_src, A.n_dec, lane, rw, lg);
                 const uint32_t out = __shfl_sync(kFull, L.out, src);
+                CT_CHECK(out < A.total && nsp_src >= 1 && nsp_src <= MM);
                 if (A.series) {
                     for (int s = 0; s < nsp_src; ++s)
                         for (int k = lane; k < A.n_dec; k += 32)

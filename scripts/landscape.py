@@ -18,6 +18,7 @@ ap.add_argument("--components", type=int, default=3)
 ap.add_argument("--limit", type=int, default=0, help="only the first K terminal states (0 = all)")
 ap.add_argument("--states-file", default="", help="gzipped list of terminal states to simulate instead of the enumeration "
                                                   "(profiles/landscape4_sample_states.txt.gz: scripts/make_landscape4_sample.py)")
+ap.add_argument("--no-motifs", action="store_true", help="skip the motif-enrichment table")
 ap.add_argument("--out", default="", help="write this rank's JSON line to <out>.rank<r>.json as well")
 args = ap.parse_args()
 rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -44,13 +45,14 @@ dt = time.perf_counter() - t0
 best = np.argsort(-res["mean"])[:5]
 # which motifs are enriched among the (topology, parameter set) pairs that oscillate? (this rank's share)
 MOTIFS = ["ABi_BCi_CAi", "ABi_BAi", "AAa", "AAi", "ABa_BAi", "ABa_BCa_CAa", "AAa_ABi_BAi", "ABi_BCi_CAa"]
-motifs = landscape_motifs(grammar, terminals, res, MOTIFS, args.n)
+motifs = None if args.no_motifs else landscape_motifs(grammar, terminals, res, MOTIFS, args.n)
 line = json.dumps({"rank": rank, "world": world, "terminal_states": len(terminals), "enumeration_s": round(t_enum, 3),
                   "states_this_rank": len(res["index"]), "trajectories": len(res["index"]) * args.n,
                   "events": int(res["events"].sum()), "seconds": round(dt, 2),
                   "reaction_steps_per_s": float(res["events"].sum() / dt),
                   "top": [[terminals[res["index"][i]], round(float(res["mean"][i]), 4), round(float(res["success"][i]), 3)] for i in best],
-                  "motif_odds_ratios": {r["pattern"]: round(float(r["odds_ratio"]), 3) for _, r in motifs.iterrows()}})
+                  "motif_odds_ratios": None if motifs is None else
+                  {r["pattern"]: round(float(r["odds_ratio"]), 3) for _, r in motifs.iterrows()}})
 print(line)
 if args.out:
     open(f"{args.out}.rank{rank}.json", "w").write(line + "\n")
