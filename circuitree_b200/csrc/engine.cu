@@ -17,6 +17,7 @@
 #include "ssa_pairwise.cuh"
 #include "ssa_dimers.cuh"
 #include "ssa_dimers_coop.cuh"
+#include "ssa_pairwise_coop.cuh"
 
 namespace {
 
@@ -557,6 +558,29 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
         eng->launches += 1;
         // (pageable host memory: the copies above have been staged when cudaMemcpyAsync returns)
         return CT_OK;
+    }
+    // Pairwise launches that fit into ONE wave of the cooperative kernel (one trajectory per sub-group of lanes,
+    // one gene per lane: ssa_pairwise_coop.cuh) last as long as their longest trajectory; its step is ~2x shorter.
+    {
+        const int G = max_nsp <= 4 ? 4 : 8;
+        const size_t csmem = ct::pair_coop_warp_bytes(G, (int)max_nsp) * (ct::kPairCoopThreads / 32);
+        int per_sm = 0;
+        if (G == 4) CT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ct::ssa_pairwise_coop_kernel<4, 4>, ct::kPairCoopThreads, csmem));
+        else CT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ct::ssa_pairwise_coop_kernel<8, 5>, ct::kPairCoopThreads, csmem));
+        const uint64_t per_cta = (uint64_t)ct::kPairCoopThreads / G;
+        uint64_t cap = (uint64_t)eng->n_sm * (per_sm > 0 ? per_sm : 1);
+        // (automatic: up to one and a half waves -- beyond that the one-lane kernels' throughput wins)
+        const bool pair_coop = per_sm > 0 && (cfg->schedule == 3 || (cfg->schedule == 0 && 2 * total <= 3 * cap * per_cta));
+        if (pair_coop) {
+            if (cfg->grid_limit > 0 && (uint64_t)cfg->grid_limit < cap) cap = (uint64_t)cfg->grid_limit;
+            const uint64_t want = (total + per_cta - 1) / per_cta;
+            const unsigned cgrid = (unsigned)(want < cap ? want : cap);
+            if (G == 4) ct::ssa_pairwise_coop_kernel<4, 4><<<cgrid, ct::kPairCoopThreads, csmem, stream>>>(A, (int)max_nsp);
+            else ct::ssa_pairwise_coop_kernel<8, 5><<<cgrid, ct::kPairCoopThreads, csmem, stream>>>(A, (int)max_nsp);
+            CT_CUDA(cudaGetLastError());
+            eng->launches += 1;
+            return CT_OK;
+        }
     }
     const int mm = max_nsp <= 3 ? 3 : (int)max_nsp;
     bool all_full = true;

@@ -85,6 +85,70 @@ def allgather_packed(buf: np.ndarray, staging: _Staging) -> tuple[np.ndarray, li
     return out, sizes, cap
 
 
+class _ExchangeThread:
+    """Runs the collectives of the statistic exchanges off the search thread, one after the other, in
+    submission order (every rank submits the same number).  A rank that reaches an exchange early keeps
+    selecting and simulating instead of waiting for the slowest rank; it merges what arrives when it
+    arrives (`RootParallelSearch._poll`)."""
+
+    def __init__(self, device):
+        import queue
+        import threading
+
+        self.device = device
+        self.staging = _Staging(device)
+        self.todo: "queue.Queue" = queue.Queue()
+        self.done: "queue.Queue" = queue.Queue()
+        self.outstanding = 0
+        self.comm_s = 0.0
+        self.error = None
+        self.thread = threading.Thread(target=self._work, daemon=True)
+        self.thread.start()
+
+    def _work(self):
+        try:
+            if self.device is not None:
+                import torch
+
+                torch.cuda.set_device(self.device)      # the current device is per thread
+            while True:
+                buf = self.todo.get()
+                if buf is None:
+                    return
+                t0 = time.perf_counter()
+                host, sizes, cap = allgather_packed(buf, self.staging)
+                parts = [host[r * cap: r * cap + sizes[r]].copy() for r in range(len(sizes))]
+                self.comm_s += time.perf_counter() - t0
+                self.done.put(parts)
+        except BaseException as e:      # surfaced by the search thread
+            self.error = e
+            self.done.put(None)
+
+    def submit(self, buf: np.ndarray) -> None:
+        self.outstanding += 1
+        self.todo.put(np.array(buf, dtype=np.int64, copy=True))
+
+    def collect(self, block: bool):
+        """Finished exchanges (lists of per-rank buffers), oldest first; all outstanding ones if `block`."""
+        import queue
+
+        out = []
+        while self.outstanding:
+            try:
+                parts = self.done.get(block=block)
+            except queue.Empty:
+                break
+            if parts is None:
+                raise RuntimeError(f"statistic exchange failed: {self.error!r}")
+            self.outstanding -= 1
+            out.append(parts)
+        return out
+
+    def close(self) -> None:
+        self.todo.put(None)
+        self.thread.join(timeout=60)
+
+
 class RootParallelSearch:
     """Drives one :class:`NativeTree` per rank with periodic statistic merges.
 
@@ -95,9 +159,15 @@ class RootParallelSearch:
         device: torch device for the collective buffers (``cuda:<local_rank>`` with NCCL, None with gloo).
         pipeline_depth: reward batches kept in flight (they stay in flight across a merge).
         max_depth: exchange only states with at most this many interactions (-1: everything).
+        overlap: True (default): the collectives run on a helper thread and a rank merges the others'
+            statistics when they arrive (at the next batch boundary) instead of blocking at the exchange --
+            measured on 8 GPUs, blocking exchanges spent 7.2 of 18.1 s waiting for the slowest rank
+            (profiles/r02_bench_n8_short.json).  False: merge at the exchange itself.  Either way every
+            replica ends with every other replica's statistics.
     """
 
-    def __init__(self, tree, sync_every: int, batch_size: int, device=None, pipeline_depth: int = 1, max_depth: int = -1):
+    def __init__(self, tree, sync_every: int, batch_size: int, device=None, pipeline_depth: int = 1, max_depth: int = -1,
+                 overlap: bool = True):
         import torch.distributed as dist
 
         self.tree = tree
@@ -114,7 +184,31 @@ class RootParallelSearch:
         self.records_merged = 0
         self.timing = {"pack_s": 0.0, "comm_s": 0.0, "merge_s": 0.0}
         self.exhausted = False            # the whole tree is exhausted (here or on another replica)
+        self.overlap = bool(overlap)
         self._staging = _Staging(device)
+        self._xthread: Optional[_ExchangeThread] = None
+
+    def _merge_parts(self, parts) -> None:
+        t0 = time.perf_counter()
+        for r, part in enumerate(parts):
+            if r == self.rank:
+                continue
+            self.records_merged += int(part[1] + part[2])
+            if self.tree.merge_packed(part):
+                self.exhausted = True
+        self.bytes_exchanged += 8 * int(sum(len(p) for p in parts))
+        self.timing["merge_s"] += time.perf_counter() - t0
+
+    def _poll(self, block: bool = False) -> None:
+        """Merge the exchanges that have completed (all outstanding ones if `block`)."""
+        if self._xthread is None:
+            return
+        t0 = time.perf_counter()
+        finished = self._xthread.collect(block)
+        if block:
+            self.timing["wait_s"] = self.timing.get("wait_s", 0.0) + time.perf_counter() - t0
+        for parts in finished:
+            self._merge_parts(parts)
 
     def sync(self) -> None:
         """One exchange.  Collective: every rank must call it the same number of times."""
@@ -124,25 +218,21 @@ class RootParallelSearch:
         send_np = self._staging.send_buffer(1 << 16).numpy()
         buf = self.tree.pack_deltas(out=send_np, max_depth=self.max_depth)
         t1 = time.perf_counter()
-        host, sizes, cap = allgather_packed(buf, self._staging)
-        t2 = time.perf_counter()
-        for r in range(self.world):
-            if r == self.rank:
-                continue
-            part = host[r * cap: r * cap + sizes[r]]
-            self.records_merged += int(part[1] + part[2])
-            if self.tree.merge_packed(part):
-                self.exhausted = True
-        t3 = time.perf_counter()
         self.timing["pack_s"] += t1 - t0
-        self.timing["comm_s"] += t2 - t1
-        self.timing["merge_s"] += t3 - t2
         self.bytes_sent += 8 * int(buf.size)
-        self.bytes_exchanged += 8 * int(sum(sizes))
         self.n_syncs += 1
+        if self.overlap:
+            if self._xthread is None:
+                self._xthread = _ExchangeThread(self.device)
+            self._xthread.submit(buf)
+            self._poll()
+            return
+        host, sizes, cap = allgather_packed(buf, self._staging)
+        self.timing["comm_s"] += time.perf_counter() - t1
+        self._merge_parts([host[r * cap: r * cap + sizes[r]] for r in range(self.world)])
 
     def run(self, n_steps_per_rank: int) -> int:
-        """``n_steps_per_rank`` iterations on this rank, a merge after every ``sync_every``; returns
+        """``n_steps_per_rank`` iterations on this rank, an exchange after every ``sync_every``; returns
         the number of iterations done (fewer only when the tree got exhausted).  Every rank runs the
         same number of exchanges whatever happens to its own search, so the collectives always match."""
         pipe = SearchPipeline(self.tree, self.batch_size, self.pipeline_depth)
@@ -150,15 +240,24 @@ class RootParallelSearch:
         try:
             while done < n_steps_per_rank:
                 k = min(self.sync_every, n_steps_per_rank - done)
-                if not self.exhausted:
+                left = k
+                while left > 0 and not self.exhausted:
+                    step = min(self.batch_size, left)
                     try:
-                        pipe.advance(k)
+                        pipe.advance(step)
                     except NativeExhaustionError:
                         self.exhausted = True
+                    left -= step
+                    self._poll()               # statistics that arrived meanwhile
                 done += k
                 if done >= n_steps_per_rank:
                     pipe.drain()               # the last exchange carries every reward
                 self.sync()
         finally:
             pipe.drain()
+            if self._xthread is not None:
+                self._poll(block=True)
+                self.timing["comm_s"] += self._xthread.comm_s
+                self._xthread.close()
+                self._xthread = None
         return pipe.done

@@ -42,9 +42,9 @@ typedef struct ct_sim_config {
     float dt;                /* seconds between grid points, default 20 */
     float init_mean;         /* Poisson mean of initial protein counts, default 10 */
     int32_t schedule;        /* 0 auto; 1 one topology per warp (big jobs); 2 mixed topologies per warp
-                                (many small jobs); 3 cooperative: several lanes share one trajectory (dimer
-                                topologies in launches too small to fill the device; same as 2 for pairwise
-                                topologies).  Results are identical, only the speed differs. */
+                                (many small jobs); 3 cooperative: a sub-group of 4 or 8 lanes shares one
+                                trajectory (launches too small to fill the device: a shorter step instead of
+                                more trajectories per warp).  Results are identical, only the speed differs. */
     int32_t lpt;             /* 1 (default): start trajectories longest-expected-first (cost pre-pass +
                                 radix sort); 0: in id order.  Results are identical. */
     int32_t grid_limit;      /* 0 (default): a launch may fill every CTA slot of the device; k > 0: at most k CTAs,

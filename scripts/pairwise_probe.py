@@ -38,6 +38,10 @@ def timed(handles, counts, cfg, label, reps=2):
 
 
 cfg = _capi.default_config()
+for k in (8, 12, 14, 16):            # small launches: one-lane kernels against the cooperative one
+    for sched in (1, 3):
+        c = _capi.default_config(); c.schedule = sched
+        timed([h], [1 << k], c, f"repressilator 2^{k} schedule {sched}", reps=1)
 timed([h], [1 << logn], cfg, f"fast loop 2^{logn}")
 gen = _capi.default_config(); gen.fast_path = 0
 timed([h], [1 << logn], gen, f"general loop 2^{logn}")
@@ -56,4 +60,9 @@ for comps in ("ABC", "ABCDE"):
         c, a, i = g.parse_genotype(t.get_random_terminal_descendant(comps + "::"))
         hs.append(_capi.compile_topology(len(c), a, i))
     uniq, counts = np.unique(np.array(hs, dtype=np.uint64), return_counts=True)
-    timed(uniq, (counts * traj).astype(np.uint32), cfg, f"mixed batch {comps}: {leaves} leaves x {traj} ({len(uniq)} topologies)")
+    for sched in (2, 3):
+        c = _capi.default_config(); c.schedule = sched
+        for frac in (8, 1):
+            sel = slice(0, max(1, len(uniq) // frac))
+            timed(uniq[sel], (counts[sel] * traj).astype(np.uint32), c,
+                  f"mixed batch {comps}: {int(counts[sel].sum())} leaves x {traj} ({len(uniq[sel])} topologies) schedule {sched}", reps=1)

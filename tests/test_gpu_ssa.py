@@ -251,13 +251,13 @@ def test_schedules_give_identical_results(eng):
     counts = rg.integers(1, 40, size=150)
     bases = np.arange(150) * 1000
     outs = []
-    for schedule in (1, 2, 0):
+    for schedule in (1, 2, 0, 3):
         c = small_cfg(nt=320, decim=16)
         c.schedule = schedule
         outs.append(gpu_run(eng, states, counts, c, seed=13, bases=bases))
     for k in ("reward", "lag", "events"):
-        assert np.array_equal(outs[0][k], outs[1][k]), k
-        assert np.array_equal(outs[0][k], outs[2][k]), k
+        for other in outs[1:]:
+            assert np.array_equal(outs[0][k], other[k]), k
     # longest-first ordering (and any cost hint) changes the launch order only
     for schedule in (1, 2):
         c = small_cfg(nt=320, decim=16)
@@ -270,6 +270,32 @@ def test_schedules_give_identical_results(eng):
     bad = _capi.default_config(); bad.schedule = 7
     with pytest.raises(_capi.EngineError):
         eng.rewards_host([handle_of("*AB::ABi")], [4], [0], bad, 1)
+
+
+def test_cooperative_pairwise_kernel_is_bit_identical_on_the_full_grid(eng, cfg):
+    """ssa_pairwise_coop_kernel (schedule 3: one trajectory per sub-group of 4 / 8 lanes, one gene per
+    lane; what schedule 0 picks for launches of at most one wave) against the one-lane kernels over whole
+    2000-point trajectories: single-regulator, mixed promoters, self-loops, 2-5 components, series too."""
+    cases = [["*ABC::ABi_BCi_CAi", "*ABC::AAa_ABi_BBa_BCi_CAi_CCa", "*AB::ABa_BAi", "*A::AAi", "*ABC::"],
+             ["*ABCD::ABa_CBi_BCa_DCi_ADi_CAa_DDa", "*ABCD::ABi_BCi_CDi_DAi"],
+             ["*ABCDE::ABi_BCi_CDi_DEi_EAi", "*ABCDE::AAa_ABi_BAa_BBi_CAi_DCa_EDi_AEa_CCi", "*ABC::ABa_CBi_BCi_CAa"]]
+    for states in cases:
+        counts = [37 + 11 * k for k in range(len(states))]
+        outs = []
+        for schedule in (3, 2, 1):
+            c = _capi.default_config()
+            c.schedule = schedule
+            outs.append(gpu_run(eng, states, counts, c, seed=41, bases=np.arange(len(states)) * 1000, series=True))
+        for k in ("reward", "lag", "events", "series"):
+            assert np.array_equal(outs[0][k], outs[1][k]) and np.array_equal(outs[0][k], outs[2][k]), (states[0], k)
+        assert outs[0]["events"].min() > 1000
+    # the automatic schedule takes the cooperative kernel for a launch of one wave and gives the same bits
+    c = _capi.default_config()
+    auto = gpu_run(eng, cases[0], [64] * 5, c, seed=43)
+    c.schedule = 1
+    one = gpu_run(eng, cases[0], [64] * 5, c, seed=43)
+    for k in ("reward", "lag", "events"):
+        assert np.array_equal(auto[k], one[k]), k
 
 
 def test_single_regulator_fast_path_is_bit_identical(eng):
