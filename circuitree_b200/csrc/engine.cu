@@ -569,8 +569,14 @@ int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n
         else CT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ct::ssa_pairwise_coop_kernel<8, 5>, ct::kPairCoopThreads, csmem));
         const uint64_t per_cta = (uint64_t)ct::kPairCoopThreads / G;
         uint64_t cap = (uint64_t)eng->n_sm * (per_sm > 0 ? per_sm : 1);
-        // (automatic: up to one and a half waves -- beyond that the one-lane kernels' throughput wins)
-        const bool pair_coop = per_sm > 0 && (cfg->schedule == 3 || (cfg->schedule == 0 && 2 * total <= 3 * cap * per_cta));
+        // Automatic choice, in waves of the cooperative kernel (28,416 trajectories for <= 4 components, 14,208 for 5), from
+        // profiles/r02_pairwise_coop_probe.txt: one job: 2^16 repressilator trajectories 206 ms vs 264 ms one-lane (2^8: 78 vs
+        // 110 ms), the one-lane loops win from ~2^17; many small jobs (MCTS batches, 32 trajectories per leaf): 3-component
+        // 955 leaves 1.06 s vs 1.61 s and 4096 leaves 1.61 s vs 2.02 s (lane utilisation 0.83 vs 0.53), 5-component 750 leaves
+        // 1.65 s vs 2.81 s but 4096 leaves 3.73 s vs 3.46 s.
+        const uint64_t wave = cap * per_cta;
+        const uint64_t limit = n_jobs > 1 ? (G == 4 ? 5 * wave : 4 * wave) : (5 * wave) / 2;
+        const bool pair_coop = per_sm > 0 && (cfg->schedule == 3 || (cfg->schedule == 0 && total <= limit));
         if (pair_coop) {
             if (cfg->grid_limit > 0 && (uint64_t)cfg->grid_limit < cap) cap = (uint64_t)cfg->grid_limit;
             const uint64_t want = (total + per_cta - 1) / per_cta;
