@@ -54,7 +54,22 @@ class _Staging:
         return self.recv
 
 
-def allgather_packed(buf: np.ndarray, staging: _Staging) -> tuple[np.ndarray, list[int], int]:
+def _gather(out, inp, poll: bool) -> None:
+    """all_gather_into_tensor; with ``poll`` the calling (helper) thread waits for completion by
+    querying, not inside a blocking CUDA call -- a thread parked in a synchronous copy behind a
+    collective that waits for a late rank slows the search thread's own launches and copies down."""
+    import torch.distributed as dist
+
+    if not poll:
+        dist.all_gather_into_tensor(out, inp)
+        return
+    work = dist.all_gather_into_tensor(out, inp, async_op=True)
+    while not work.is_completed():
+        time.sleep(0.0005)
+    work.wait()
+
+
+def allgather_packed(buf: np.ndarray, staging: _Staging, poll: bool = False) -> tuple[np.ndarray, list[int], int]:
     """All-gather one packed delta buffer per rank.  ``buf`` must be a view of
     ``staging.send_buffer``'s numpy array (or any int64 array; it is copied in then).  Returns
     (host array of ``world * cap`` words, per-rank sizes, cap)."""
@@ -66,7 +81,7 @@ def allgather_packed(buf: np.ndarray, staging: _Staging) -> tuple[np.ndarray, li
     n = int(buf.size)
     size = torch.tensor([n], dtype=torch.int64, device=dev)
     sizes_t = torch.empty(world, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(sizes_t, size)
+    _gather(sizes_t, size, poll)
     sizes = [int(x) for x in sizes_t.cpu().tolist()]
     cap = max(sizes)
     send = staging.send_buffer(cap)
@@ -75,7 +90,7 @@ def allgather_packed(buf: np.ndarray, staging: _Staging) -> tuple[np.ndarray, li
         send_np[:n] = buf
     mine = send[:cap].to(dev, non_blocking=True) if dev.type == "cuda" else send[:cap]
     gathered = torch.empty(world * cap, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(gathered, mine)
+    _gather(gathered, mine, poll)
     if dev.type == "cuda":
         host = staging.recv_buffer(world * cap)
         host[: world * cap].copy_(gathered)            # device -> pinned host, synchronous for the caller
@@ -116,7 +131,7 @@ class _ExchangeThread:
                 if buf is None:
                     return
                 t0 = time.perf_counter()
-                host, sizes, cap = allgather_packed(buf, self.staging)
+                host, sizes, cap = allgather_packed(buf, self.staging, poll=True)
                 parts = [host[r * cap: r * cap + sizes[r]].copy() for r in range(len(sizes))]
                 self.comm_s += time.perf_counter() - t0
                 self.done.put(parts)
