@@ -33,17 +33,19 @@ for k in hdr:
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 try:
     srows = list(csv.reader(io.StringIO(src)))
-    sh = srows[0]
+    hi = next(i for i, r in enumerate(srows) if r and r[0] == "Address")      # (row 0 names the kernel)
+    sh = srows[hi]
     col = {n: i for i, n in enumerate(sh)}
-    samp = next((c for c in sh if c.startswith("# Samples") or c == "Warp Stall Sampling (All Samples)" or c.startswith("Warp Stall Sampling (All")), None)
-    inst = next((c for c in sh if c.startswith("# Instructions Executed") or c == "Instructions Executed"), None)
-    text = next((c for c in sh if c in ("Source", "SASS")), sh[1])
-    if samp:
-        body = [r for r in srows[1:] if len(r) == len(sh)]
-        tot = sum(float(r[col[samp]] or 0) for r in body) or 1.0
-        top = sorted(body, key=lambda r: -float(r[col[samp]] or 0))[:25]
-        print(f"\n# 25 most-sampled instructions (of {tot:.0f} warp-state samples)")
-        for r in top:
-            print(f"{float(r[col[samp]] or 0) / tot * 100:5.1f}%  {r[col[text]][:110]}")
+    body = [r for r in srows[hi + 1:] if len(r) >= len(sh) - 1 and r[0].startswith("0x")]
+    samp, inst = col["# Samples"], col["Instructions Executed"]
+    tot = sum(float(r[samp] or 0) for r in body) or 1.0
+    tot_inst = sum(float(r[inst] or 0) for r in body) or 1.0
+    print(f"\n# SASS instructions: {len(body)}; warp instructions executed {tot_inst:.4g}; warp-state samples {tot:.0f}")
+    print("# 30 most-sampled instructions: share of samples, share of executed instructions, avg threads, top stall, SASS")
+    stalls = [c for c in sh if c.startswith("stall_") and "Not Issued" not in c]
+    for r in sorted(body, key=lambda r: -float(r[samp] or 0))[:30]:
+        top = max(stalls, key=lambda c: float(r[col[c]] or 0))
+        print(f"{float(r[samp] or 0) / tot * 100:5.1f}%  {float(r[inst] or 0) / tot_inst * 100:5.2f}%  {r[col['Avg. Threads Executed']]:>4}  "
+              f"{top[6:]:<18} {r[col['Source']].strip()[:90]}")
 except Exception as e:      # the source page is optional
     print("# (source page not parsed:", e, ")")
