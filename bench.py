@@ -513,25 +513,28 @@ def main() -> None:
 
     # ---- config 3 (bounded): DimersGrammar search, five TFs -------------------------------------------------
     if "dimer_search" in legs:
-        from circuitree_b200 import OscillationTree
-
         dg = DimersGrammar(components=list("ABC"), regulators=list("DE"), interactions=["activates", "inhibits"])
-        dtree = OscillationTree(grammar=dg, root="ABC+DE::", seed=rank, n_exhausted=np.inf, trajectories_per_reward=args.mcts_traj,
-                                device=local_rank)
-        dtree.search_mcts_batched(64, 64)                                        # warm-up
+        dtree = NativeTree(dg, "ABC+DE::", seed=rank, n_exhausted=np.inf, trajectories_per_reward=args.mcts_traj, device=local_rank,
+                           reward_seed=300 + rank)
+        dtree.search_mcts(64, batch_size=64)                                     # warm-up
+        dtree.timing = {k: 0.0 for k in dtree.timing}
         e0, s0 = dtree.reward_engine.total_events, dtree.reward_engine.total_issue_slots
         barrier()
         t0 = time.perf_counter()
-        dtree.search_mcts_batched(args.dimer_search_rollouts, 1024, pipeline_depth=4)
+        dtree.search_mcts(args.dimer_search_rollouts, batch_size=1024, pipeline_depth=4)
         barrier()
         secs = time.perf_counter() - t0
         (secs,), (ev, slots) = over_ranks([secs], [dtree.reward_engine.total_events - e0, dtree.reward_engine.total_issue_slots - s0])
         line["dimer_search"] = {"metric": "mcts_rollouts_per_s", "value": world * args.dimer_search_rollouts / secs, "unit": "rollouts/s",
                                 "reaction_steps_per_s": ev / secs, "roofline_frac": slots / secs / world / 1e12 / peak,
-                                "config": {"workload": f"DimersGrammar ABC+DE (five TFs) oscillation search, {args.dimer_search_rollouts} "
-                                                       f"rollouts per GPU (independent trees), {args.mcts_traj} trajectories per rollout, "
-                                                       "1024 leaves per launch, 4 launches in flight; the full 10^5-rollout run is "
-                                                       "scripts/dimer_search.py (profiles/)"}}
+                                "host_seconds_rank0": {k: round(v, 3) for k, v in dtree.timing.items()},
+                                "config": {"workload": f"DimersGrammar ABC+DE (five TFs) oscillation search on the native tree, "
+                                                       f"{args.dimer_search_rollouts} rollouts per GPU (independent trees), "
+                                                       f"{args.mcts_traj} trajectories per rollout, 1024 leaves per launch, 4 launches "
+                                                       "in flight: ONE round of launches, i.e. as long as its longest trajectory; the "
+                                                       "sustained rate is the 10^5-rollout run of scripts/dimer_search.py "
+                                                       "(profiles/r02_dimer_search_100k.json: 225 rollouts/s)"}}
+        del dtree
 
     # ---- config 5 (bounded sample): exhaustive 3-component landscape, sharded over ranks -------------------
     if "landscape" in legs:

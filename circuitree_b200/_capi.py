@@ -87,6 +87,7 @@ def lib() -> ctypes.CDLL:
     L.ct_engine_destroy.argtypes = [vp]
     L.ct_engine_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]
     L.ct_compile_topology.argtypes = [i32, vp, i32, vp, i32, i32, ctypes.POINTER(u64)]
+    L.ct_topology_info.argtypes = [u64, ctypes.POINTER(i32), ctypes.POINTER(i32)]
     L.ct_launch_rewards.argtypes = [vp, vp, vp, vp, vp, i32, ctypes.POINTER(SimConfig), u64, vp, vp, vp, vp, vp, vp, i32]
     L.ct_reduce_jobs.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     L.ct_rewards_host.argtypes = [vp, vp, vp, vp, vp, i32, ctypes.POINTER(SimConfig), u64, vp, vp, vp, vp, vp]
@@ -97,7 +98,7 @@ def lib() -> ctypes.CDLL:
     L.ct_engine_launch_count.argtypes = [vp]
     L.ct_engine_warp_iterations.restype = i64
     L.ct_engine_warp_iterations.argtypes = [vp]
-    for name in ("ct_default_config", "ct_engine_create", "ct_engine_destroy", "ct_engine_info",
+    for name in ("ct_topology_info", "ct_default_config", "ct_engine_create", "ct_engine_destroy", "ct_engine_info",
                  "ct_compile_topology", "ct_launch_rewards", "ct_reduce_jobs", "ct_rewards_host",
                  "ct_reward_from_series_host", "ct_rewards_submit", "ct_rewards_wait"):
         getattr(L, name).restype = ctypes.c_int
@@ -136,6 +137,13 @@ def compile_topology(n_species: int, activations, inhibitions, k: int = 2) -> in
     check(lib().ct_compile_topology(n_species, act.ctypes.data, act.shape[0], inh.ctypes.data, inh.shape[0], k,
                                     ctypes.byref(h)))
     return int(h.value)
+
+
+def topology_info(handle: int) -> tuple[int, int]:
+    """(species, reactions) of a compiled topology (``ct_topology_info``)."""
+    nsp, nr = ctypes.c_int32(0), ctypes.c_int32(0)
+    check(lib().ct_topology_info(int(handle), ctypes.byref(nsp), ctypes.byref(nr)))
+    return int(nsp.value), int(nr.value)
 
 
 def _ptr(a):

@@ -371,6 +371,26 @@ int ct_compile_topology(int32_t n_species, const int64_t* act, int32_t n_act, co
     return CT_OK;
 }
 
+int ct_topology_info(uint64_t handle, int32_t* n_species, int32_t* n_reactions)
+{
+    if (is_dimer_handle(handle)) {
+        std::lock_guard<std::mutex> lock(g_dimer_mutex);
+        const uint64_t idx = handle & 0xffffffffull;
+        if (idx >= g_dimer_topos.size()) return fail(CT_ERR_INVALID, "unknown dimer topology handle");
+        const ct::DimerTopo& T = g_dimer_topos[idx];
+        if (n_species) *n_species = T.n_tf;
+        if (n_reactions) *n_reactions = 4 * T.n_tf + 2 * T.n_ixn + 2 * T.n_dim;
+        return CT_OK;
+    }
+    const uint32_t nsp = ct::topo_nspecies(handle);
+    if (nsp < 1 || nsp > CT_MAX_SPECIES) return fail(CT_ERR_INVALID, "bad topology handle");
+    int edges = 0;
+    for (int c = 0; c < 25; ++c) edges += ((handle >> (2 * c)) & 3u) != 0;
+    if (n_species) *n_species = (int32_t)nsp;
+    if (n_reactions) *n_reactions = 4 * (int32_t)nsp + 2 * edges;
+    return CT_OK;
+}
+
 int ct_launch_rewards(ct_engine* eng, const uint64_t* handles, const uint32_t* n_traj, const uint64_t* traj_base,
                       const float* job_cost, int32_t n_jobs, const ct_sim_config* cfg, uint64_t seed, void* stream_,
                       const float* d_params, float* d_reward, int32_t* d_lag, uint32_t* d_events, uint8_t* d_series,

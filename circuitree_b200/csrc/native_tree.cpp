@@ -132,9 +132,181 @@ struct Edge {
     double unc_reward = 0.0;                // because the child is flagged exhausted (root-parallel replicas)
 };
 
+// ---- DimersGrammar states (reference circuitree/models.py:524-939; semantics = this repo's Python mirror,
+// circuitree_b200/models.py, which restates the documented intent where upstream raises) ----
+// A state is the sorted list of its interactions; an interaction "m1 m2 type target" (monomers sorted) is a
+// small integer code whose numeric order is the ASCII order of the four characters, so comparing code lists
+// lexicographically is comparing the reference's interaction strings.  Lists are interned: a tree key is the
+// list's id (+ the terminal bit), which keeps the tree code of the pairwise grammar unchanged.
+struct DimerSpace {
+    int S = 0, C = 0, T = 0;                 // species (components + regulators), components, interaction types
+    char letter[kMaxN];                      // species rank (ASCII order) -> letter
+    bool is_comp[kMaxN];
+    int comp_pos[kMaxN], reg_pos[kMaxN];     // species rank -> index in the sorted components / regulators string
+    int decl_comp[kMaxN];                    // component declaration index -> species rank
+    char type_letter[3];                     // type rank (ASCII order) -> letter
+    int decl_type[3];                        // declaration index -> type rank
+    int max_interactions = 0, max_per_promoter = 2;
+    std::vector<std::pair<int, int>> dimers; // valid dimers (m1 <= m2 as species ranks) in ASCII order of the two letters
+    std::vector<std::vector<uint16_t>> remap;    // relabelling (component perm x regulator perm) -> code -> code
+    std::vector<std::vector<uint16_t>> lists;    // interned interaction lists (sorted codes)
+    std::unordered_map<std::string, uint32_t> ids;
+    std::unordered_map<uint32_t, uint32_t> canon_memo;
+    std::string comps_sorted, regs_sorted;
+
+    int code_of(int m1, int m2, int type, int target) const { return ((m1 * S + m2) * T + type) * S + target; }
+    void decode(int code, int& m1, int& m2, int& type, int& target) const
+    {
+        target = code % S; code /= S;
+        type = code % T; code /= T;
+        m2 = code % S; m1 = code / S;
+    }
+    uint32_t intern(const std::vector<uint16_t>& v)
+    {
+        std::string k(reinterpret_cast<const char*>(v.data()), v.size() * sizeof(uint16_t));
+        auto it = ids.find(k);
+        if (it != ids.end()) return it->second;
+        const uint32_t id = (uint32_t)lists.size();
+        lists.push_back(v);
+        ids.emplace(std::move(k), id);
+        return id;
+    }
+    uint32_t canonical(uint32_t id)
+    {
+        auto it = canon_memo.find(id);
+        if (it != canon_memo.end()) return it->second;
+        const std::vector<uint16_t> src = lists[id];
+        std::vector<uint16_t> best, cur(src.size());
+        bool first = true;
+        for (const auto& map : remap) {
+            for (size_t x = 0; x < src.size(); ++x) cur[x] = map[src[x]];
+            std::sort(cur.begin(), cur.end());
+            if (first || cur < best) { best = cur; first = false; }
+        }
+        const uint32_t out = intern(best);
+        canon_memo.emplace(id, out);
+        return out;
+    }
+    // action ids: 0 = *terminate*, 1 + ((dimer * C + declared component) * T + declared type)
+    void actions(uint64_t key, std::vector<int>& out) const
+    {
+        out.clear();
+        if (key & kTerminalBit) return;
+        const std::vector<uint16_t>& v = lists[(size_t)(key & 0xffffffffull)];
+        // triplets (dimer, target) in use, letters in use, load per promoter
+        bool in_use[kMaxN] = {false, false, false, false, false};
+        int load[kMaxN] = {0, 0, 0, 0, 0};
+        std::vector<int> trip;
+        for (uint16_t c : v) {
+            int m1, m2, ty, tg;
+            decode(c, m1, m2, ty, tg);
+            in_use[m1] = in_use[m2] = in_use[tg] = true;
+            load[tg] += 1;
+            const int t3 = (m1 * S + m2) * S + tg;
+            if (std::find(trip.begin(), trip.end(), t3) == trip.end()) trip.push_back(t3);
+        }
+        if ((int)trip.size() >= max_interactions) { out.push_back(0); return; }
+        if (!trip.empty()) out.push_back(0);
+        for (size_t d = 0; d < dimers.size(); ++d)
+            for (int dc = 0; dc < C; ++dc) {
+                const int m1 = dimers[d].first, m2 = dimers[d].second, tg = decl_comp[dc];
+                if (!trip.empty()) {
+                    if (load[tg] >= max_per_promoter) continue;
+                    if (std::find(trip.begin(), trip.end(), (m1 * S + m2) * S + tg) != trip.end()) continue;
+                    if (!in_use[m1] && !in_use[m2] && !in_use[tg]) continue;
+                }
+                for (int t = 0; t < T; ++t) out.push_back(1 + ((int)d * C + dc) * T + t);
+            }
+    }
+    uint64_t apply(uint64_t key, int action)
+    {
+        if (action == 0) return key | kTerminalBit;
+        const int a = action - 1, t = a % T, dc = (a / T) % C, d = a / (T * C);
+        std::vector<uint16_t> v = lists[(size_t)(key & 0xffffffffull)];
+        v.push_back((uint16_t)code_of(dimers[(size_t)d].first, dimers[(size_t)d].second, decl_type[t], decl_comp[dc]));
+        std::sort(v.begin(), v.end());
+        return (key & kTerminalBit) | intern(v);
+    }
+    uint64_t step(uint64_t key, int action)
+    {
+        const uint64_t k = apply(key, action);
+        return (k & kTerminalBit) | canonical((uint32_t)(k & 0xffffffffull));
+    }
+    std::string to_string(uint64_t key) const
+    {
+        std::string s;
+        if (key & kTerminalBit) s += '*';
+        s += comps_sorted; s += '+'; s += regs_sorted; s += "::";
+        const std::vector<uint16_t>& v = lists[(size_t)(key & 0xffffffffull)];
+        for (size_t x = 0; x < v.size(); ++x) {
+            int m1, m2, ty, tg;
+            decode(v[x], m1, m2, ty, tg);
+            if (x) s += '_';
+            s += letter[m1]; s += letter[m2]; s += type_letter[ty]; s += letter[tg];
+        }
+        return s;
+    }
+    int rank_of(char c) const
+    {
+        for (int i = 0; i < S; ++i) if (letter[i] == c) return i;
+        return -1;
+    }
+    bool from_string(const char* str, uint64_t* out)
+    {
+        const char* p = str;
+        uint64_t flags = 0;
+        if (*p == '*') { flags = kTerminalBit; ++p; }
+        const std::string head = comps_sorted + "+" + regs_sorted + "::";
+        // components and regulators may come in any order, but all must be present
+        const char* sep = strstr(p, "::");
+        if (!sep) return false;
+        std::string given(p, sep);
+        const size_t plus = given.find('+');
+        if (plus == std::string::npos) return false;
+        std::string gc = given.substr(0, plus), gr = given.substr(plus + 1);
+        std::sort(gc.begin(), gc.end()); std::sort(gr.begin(), gr.end());
+        if (gc != comps_sorted || gr != regs_sorted) return false;
+        p = sep + 2;
+        std::vector<uint16_t> v;
+        while (*p) {
+            if (strlen(p) < 4) return false;
+            int m1 = rank_of(p[0]), m2 = rank_of(p[1]), tg = rank_of(p[3]), ty = -1;
+            for (int t = 0; t < T; ++t) if (type_letter[t] == p[2]) ty = t;
+            if (m1 < 0 || m2 < 0 || tg < 0 || ty < 0 || !is_comp[tg]) return false;
+            if (m1 > m2) std::swap(m1, m2);
+            v.push_back((uint16_t)code_of(m1, m2, ty, tg));
+            p += 4;
+            if (*p == '_') ++p; else if (*p) return false;
+        }
+        std::sort(v.begin(), v.end());
+        *out = flags | intern(v);
+        return true;
+    }
+    // GPU topology handle (ct_compile_topology, k = 3): rows (monomer1, monomer2, target) index components + regulators
+    bool to_handle(uint64_t key, uint64_t* handle) const
+    {
+        const std::vector<uint16_t>& v = lists[(size_t)(key & 0xffffffffull)];
+        std::vector<int64_t> act, inh;
+        for (uint16_t c : v) {
+            int m1, m2, ty, tg;
+            decode(c, m1, m2, ty, tg);
+            auto pos = [&](int r) { return (int64_t)(is_comp[r] ? comp_pos[r] : C + reg_pos[r]); };
+            int64_t a = pos(m1), b = pos(m2);
+            if (a > b) std::swap(a, b);
+            std::vector<int64_t>& dst = type_letter[ty] == 'a' ? act : inh;
+            if (type_letter[ty] != 'a' && type_letter[ty] != 'i') return false;
+            dst.push_back(a); dst.push_back(b); dst.push_back(pos(tg));
+        }
+        return ct_compile_topology(S, act.data(), (int32_t)(act.size() / 3), inh.data(), (int32_t)(inh.size() / 3), 3, handle) == CT_OK;
+    }
+    int depth_of(uint64_t key) const { return (int)lists[(size_t)(key & 0xffffffffull)].size() + ((key & kTerminalBit) ? 1 : 0); }
+};
+
 }  // namespace
 
 struct ct_tree {
+    DimerSpace* dim = nullptr;         // non-null: a DimersGrammar tree (keys are interned list ids)
+    ~ct_tree() { delete dim; }
     int n = 0, n_types = 0, n_cells = 0, max_interactions = 0;
     char comp_letter[kMaxN];       // sorted index -> letter
     int decl_comp[kMaxN];          // declaration index -> sorted index
@@ -163,6 +335,7 @@ struct ct_tree {
 
     uint64_t canonical(uint64_t key)
     {
+        if (dim) return (key & kTerminalBit) | dim->canonical((uint32_t)(key & 0xffffffffull));
         const uint64_t flags = key & kTerminalBit;
         const uint64_t body = key & ~kTerminalBit;
         auto it = canon_memo.find(body);
@@ -186,6 +359,7 @@ struct ct_tree {
     // action ids: 0 = *terminate*, 1 + (decl_pair * n_types + decl_type) = add interaction
     void actions(uint64_t key, std::vector<int>& out) const
     {
+        if (dim) { dim->actions(key, out); return; }
         out.clear();
         if (key & kTerminalBit) return;
         int n_ixn = 0;
@@ -212,7 +386,7 @@ struct ct_tree {
         const int sh = shift(si * n + sj);
         return (key & ~(3ull << sh)) | ((uint64_t)decl_type[t] << sh);
     }
-    uint64_t step(uint64_t key, int action) { return canonical(apply(key, action)); }
+    uint64_t step(uint64_t key, int action) { return dim ? dim->step(key, action) : canonical(apply(key, action)); }
 
     int node_of(uint64_t key) const
     {
@@ -304,6 +478,7 @@ struct ct_tree {
     // number of interactions of a state (+1 for a terminal state): its depth below the root
     int depth_of(uint64_t key) const
     {
+        if (dim) return dim->depth_of(key);
         int d = (key & kTerminalBit) ? 1 : 0;
         for (int c = 0; c < n_cells; ++c) d += cell(key, c) != 3u;
         return d;
@@ -374,6 +549,7 @@ struct ct_tree {
 
     std::string to_string(uint64_t key) const
     {
+        if (dim) return dim->to_string(key);
         std::string s;
         if (key & kTerminalBit) s += '*';
         for (int i = 0; i < n; ++i) s += comp_letter[i];
@@ -392,6 +568,7 @@ struct ct_tree {
     }
     bool from_string(const char* str, uint64_t* out)
     {
+        if (dim) return dim->from_string(str, out);
         const char* p = str;
         uint64_t key = all_absent;
         if (*p == '*') { key |= kTerminalBit; ++p; }
@@ -419,6 +596,7 @@ struct ct_tree {
     // GPU topology handle (ct_compile_topology layout): type letter 'a' -> 1, 'i' -> 2
     bool to_handle(uint64_t key, uint64_t* handle) const
     {
+        if (dim) return dim->to_handle(key, handle);
         uint64_t h = (uint64_t)n << 56;
         for (int c = 0; c < n_cells; ++c) {
             const uint32_t v = cell(key, c);
@@ -477,6 +655,85 @@ int ct_tree_create(const char* components, const char* types, int32_t max_intera
     if (t->to_string(rk) != root) {
         delete t;
         return tfail(CT_ERR_UNSUPPORTED, "root '%s' is not in sorted form (expected '%s')", root, t->to_string(rk).c_str());
+    }
+    t->root_key = rk;
+    t->add_node(rk);
+    *out = t;
+    return CT_OK;
+}
+
+/* A tree over DimersGrammar states (reference circuitree/models.py:524-939; semantics of this repo's Python
+ * mirror).  components / regulators / types: one character each, in declaration order; the root holds every
+ * component and regulator in sorted form ("ABC+DE::").  At most 5 TFs in total. */
+int ct_tree_create_dimers(const char* components, const char* regulators, const char* types, int32_t max_interactions,
+                          int32_t max_per_promoter, const char* root, double exploration_constant, double n_exhausted,
+                          ct_tree** out)
+{
+    if (!components || !regulators || !types || !root || !out) return tfail(CT_ERR_INVALID, "NULL argument");
+    const int C = (int)strlen(components), R = (int)strlen(regulators), T = (int)strlen(types), S = C + R;
+    if (C < 1 || S > kMaxN) return tfail(CT_ERR_UNSUPPORTED, "native dimer tree supports 1..5 TFs in total, got %d + %d", C, R);
+    if (T < 1 || T > 3) return tfail(CT_ERR_UNSUPPORTED, "native tree supports 1..3 interaction types, got %d", T);
+    std::string all = std::string(components) + regulators, st(types);
+    std::sort(all.begin(), all.end());
+    std::sort(st.begin(), st.end());
+    if (std::adjacent_find(all.begin(), all.end()) != all.end() || std::adjacent_find(st.begin(), st.end()) != st.end())
+        return tfail(CT_ERR_INVALID, "component / regulator / interaction codes must be unique");
+    ct_tree* t = new ct_tree();
+    DimerSpace* D = t->dim = new DimerSpace();
+    D->S = S; D->C = C; D->T = T;
+    D->comps_sorted = components; D->regs_sorted = regulators;
+    std::sort(D->comps_sorted.begin(), D->comps_sorted.end());
+    std::sort(D->regs_sorted.begin(), D->regs_sorted.end());
+    for (int i = 0; i < S; ++i) {
+        D->letter[i] = all[(size_t)i];
+        const size_t cp = D->comps_sorted.find(all[(size_t)i]);
+        D->is_comp[i] = cp != std::string::npos;
+        D->comp_pos[i] = D->is_comp[i] ? (int)cp : -1;
+        D->reg_pos[i] = D->is_comp[i] ? -1 : (int)D->regs_sorted.find(all[(size_t)i]);
+    }
+    for (int i = 0; i < C; ++i) D->decl_comp[i] = (int)all.find(components[i]);
+    for (int i = 0; i < T; ++i) { D->type_letter[i] = st[(size_t)i]; D->decl_type[i] = (int)st.find(types[i]); }
+    D->max_interactions = max_interactions < 0 ? C * S * S : max_interactions;
+    D->max_per_promoter = max_per_promoter;
+    // dimers in ASCII order: both monomers components, or one component and one regulator (reference models.py:596-612)
+    for (int a = 0; a < S; ++a)
+        for (int b = a; b < S; ++b)
+            if (D->is_comp[a] || D->is_comp[b]) D->dimers.emplace_back(a, b);
+    // relabellings: every permutation of the components combined with every permutation of the regulators
+    std::vector<int> cs, rs;
+    for (int i = 0; i < S; ++i) (D->is_comp[i] ? cs : rs).push_back(i);
+    std::vector<int> cperm = cs;
+    const int n_codes = S * S * T * S;
+    do {
+        std::vector<int> rperm = rs;
+        do {
+            int to[kMaxN];
+            for (size_t x = 0; x < cs.size(); ++x) to[cs[x]] = cperm[x];
+            for (size_t x = 0; x < rs.size(); ++x) to[rs[x]] = rperm[x];
+            std::vector<uint16_t> map((size_t)n_codes, 0);
+            for (int code = 0; code < n_codes; ++code) {
+                int m1, m2, ty, tg;
+                D->decode(code, m1, m2, ty, tg);
+                int a = to[m1], b = to[m2];
+                if (a > b) std::swap(a, b);
+                map[(size_t)code] = (uint16_t)D->code_of(a, b, ty, to[tg]);
+            }
+            D->remap.push_back(std::move(map));
+        } while (std::next_permutation(rperm.begin(), rperm.end()));
+    } while (std::next_permutation(cperm.begin(), cperm.end()));
+    t->n = S; t->n_types = T;
+    t->c_ucb = exploration_constant;
+    t->track_exhaustion = !std::isnan(n_exhausted);
+    t->n_exhausted = n_exhausted;
+    uint64_t rk;
+    if (!D->from_string(root, &rk)) {
+        delete t;
+        return tfail(CT_ERR_UNSUPPORTED, "root '%s' must contain every component and regulator exactly once", root);
+    }
+    if (D->to_string(rk) != root) {
+        const std::string want = D->to_string(rk);
+        delete t;
+        return tfail(CT_ERR_UNSUPPORTED, "root '%s' is not in sorted form (expected '%s')", root, want.c_str());
     }
     t->root_key = rk;
     t->add_node(rk);
@@ -702,6 +959,7 @@ int ct_tree_pack_deltas(ct_tree* t, int32_t max_depth, int64_t* buf, int64_t cap
 {
     NvtxRange nvtx_range("ct_tree_pack_deltas");
     if (!t || !n_words) return tfail(CT_ERR_INVALID, "NULL argument");
+    if (t->dim) return tfail(CT_ERR_UNSUPPORTED, "DimersGrammar trees cannot be exchanged between replicas: their keys are process-local ids");
     if (t->track_exhaustion) t->settle_exhausted();
     auto wanted = [&](uint64_t key) { return max_depth < 0 || t->depth_of(key) <= max_depth; };
     int64_t nn = 0, ne = 0;
@@ -744,6 +1002,7 @@ int ct_tree_merge_packed(ct_tree* t, const int64_t* buf, int64_t n_words, int32_
 {
     NvtxRange nvtx_range("ct_tree_merge_packed");
     if (!t || !buf) return tfail(CT_ERR_INVALID, "NULL argument");
+    if (t->dim) return tfail(CT_ERR_UNSUPPORTED, "DimersGrammar trees cannot be exchanged between replicas: their keys are process-local ids");
     if (n_words < kPackHeader || buf[0] != kPackMagic) return tfail(CT_ERR_INVALID, "not a delta buffer");
     const int64_t nn = buf[1], ne = buf[2], nx = buf[3];
     if (nn < 0 || ne < 0 || nx < 0 || kPackHeader + 3 * nn + 4 * ne + nx > n_words)

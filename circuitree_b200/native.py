@@ -17,7 +17,7 @@ from typing import Callable, Optional, Sequence
 import numpy as np
 
 from . import _capi
-from .models import SimpleNetworkGrammar
+from .models import DimersGrammar, SimpleNetworkGrammar
 
 __all__ = ["NativeTree", "NativeExhaustionError", "SearchPipeline"]
 
@@ -35,6 +35,8 @@ def _lib():
         vp, i32, i64, u64, dbl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_double
         L.ct_tree_last_error.restype = ctypes.c_char_p
         L.ct_tree_create.argtypes = [ctypes.c_char_p, ctypes.c_char_p, i32, ctypes.c_char_p, dbl, dbl, ctypes.POINTER(vp)]
+        L.ct_tree_create_dimers.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, i32, i32, ctypes.c_char_p, dbl, dbl,
+                                            ctypes.POINTER(vp)]
         L.ct_tree_destroy.argtypes = [vp]
         L.ct_tree_set_rng.argtypes = [vp, vp, vp, i32, ctypes.c_uint32]
         L.ct_tree_get_rng.argtypes = [vp, vp, vp, ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_uint32)]
@@ -53,7 +55,7 @@ def _lib():
         L.ct_tree_grow.argtypes = [vp]
         L.ct_tree_pack_deltas.argtypes = [vp, i32, vp, i64, ctypes.POINTER(i64)]
         L.ct_tree_merge_packed.argtypes = [vp, vp, i64, ctypes.POINTER(i32)]
-        for name in ("ct_tree_create", "ct_tree_destroy", "ct_tree_set_rng", "ct_tree_get_rng", "ct_tree_set_log_table",
+        for name in ("ct_tree_create", "ct_tree_create_dimers", "ct_tree_destroy", "ct_tree_set_rng", "ct_tree_get_rng", "ct_tree_set_log_table",
                      "ct_tree_rng_draw", "ct_tree_select", "ct_tree_backprop", "ct_tree_pending", "ct_tree_size",
                      "ct_tree_export", "ct_tree_key_to_string", "ct_tree_string_to_key", "ct_tree_actions",
                      "ct_tree_do_action", "ct_tree_key_to_handle", "ct_tree_grow", "ct_tree_pack_deltas",
@@ -77,8 +79,9 @@ class NativeTree:
     """MCTS on the native tree.  Rewards come from ``reward_fn(states) -> list[float]`` (any
     callable, e.g. a test stub) or, by default, from the GPU :class:`RewardEngine`.
 
-    Args mirror ``CircuiTree`` (reference circuitree.py:76-127): ``grammar`` must be a
-    :class:`SimpleNetworkGrammar` whose root holds every component.
+    Args mirror ``CircuiTree`` (reference circuitree.py:76-127): ``grammar`` is a
+    :class:`SimpleNetworkGrammar` or a :class:`DimersGrammar` whose root holds every component (and
+    regulator), e.g. ``"ABC::"`` / ``"ABC+DE::"``.
     """
 
     def __init__(self, grammar: SimpleNetworkGrammar, root: str, exploration_constant: Optional[float] = None,
@@ -97,8 +100,15 @@ class NativeTree:
         types = "".join(x[0].lower() for x in grammar.interactions)
         self._h = ctypes.c_void_p(None)
         n_exh = float("nan") if n_exhausted is None else float(n_exhausted)
-        _check(_lib().ct_tree_create(comps.encode(), types.encode(), int(grammar.max_interactions), root.encode(),
-                                     self.exploration_constant, n_exh, ctypes.byref(self._h)))
+        self.is_dimers = isinstance(grammar, DimersGrammar)
+        if self.is_dimers:
+            regs = "".join(r[0].upper() for r in grammar.regulators)
+            _check(_lib().ct_tree_create_dimers(comps.encode(), regs.encode(), types.encode(), int(grammar.max_interactions),
+                                                int(grammar.max_interactions_per_promoter), root.encode(),
+                                                self.exploration_constant, n_exh, ctypes.byref(self._h)))
+        else:
+            _check(_lib().ct_tree_create(comps.encode(), types.encode(), int(grammar.max_interactions), root.encode(),
+                                         self.exploration_constant, n_exh, ctypes.byref(self._h)))
         with np.errstate(divide="ignore"):
             table = np.log(np.arange(max_steps_hint + 1))     # numpy's own log, as the reference uses
         _check(_lib().ct_tree_set_log_table(self._h, table.ctypes.data, len(table)))
@@ -163,14 +173,19 @@ class NativeTree:
     def get_actions(self, state: str) -> list[str]:
         key = self.string_to_key(state, canonical=False)
         n = ctypes.c_int32(0)
-        ids = np.zeros(128, dtype=np.int32)
-        _check(_lib().ct_tree_actions(self._h, key, ids.ctypes.data, 128, ctypes.byref(n)))
+        ids = np.zeros(512, dtype=np.int32)
+        _check(_lib().ct_tree_actions(self._h, key, ids.ctypes.data, 512, ctypes.byref(n)))
         comps = [c[0].upper() for c in self.grammar.components]
         types = [x[0].lower() for x in self.grammar.interactions]
+        dimers = self.grammar.dimer_options if self.is_dimers else None
         out = []
         for a in ids[: n.value]:
             if a == 0:
                 out.append("*terminate*")
+            elif self.is_dimers:        # 1 + ((dimer * C + declared component) * T + declared type)
+                a -= 1
+                t, dc, d = a % len(types), (a // len(types)) % len(comps), a // (len(types) * len(comps))
+                out.append(dimers[d] + types[t] + comps[dc])
             else:
                 a -= 1
                 t, pair = a % len(types), a // len(types)

@@ -109,10 +109,13 @@ class RewardEngine:
             r, m = pairwise_shape(handles)
             self.total_issue_slots += float((job_events.astype(np.float64) * _capi_defaults.i_step(r, m)).sum())
         else:
-            shape = np.array([self._dimer_shape.get(int(h), (0, 0)) for h in handles], dtype=np.float64)
-            known = shape[:, 0] > 0
-            self.total_issue_slots += float((job_events.astype(np.float64)[known] *
-                                             _capi_defaults.i_step_dimers(shape[known, 0], shape[known, 1])).sum())
+            for h in handles:
+                if int(h) not in self._dimer_shape:       # (handles that came from the native tree)
+                    n_tf, n_r = _capi.topology_info(int(h))
+                    self._dimer_shape[int(h)] = (n_r, n_tf)
+            shape = np.array([self._dimer_shape[int(h)] for h in handles], dtype=np.float64)
+            self.total_issue_slots += float((job_events.astype(np.float64) *
+                                             _capi_defaults.i_step_dimers(shape[:, 0], shape[:, 1])).sum())
 
     # -- asynchronous batches of leaves (pipelined MCTS) ---------------------------------------------------
     def submit_leaves(self, handles: np.ndarray, trajectories_per_leaf: int) -> dict:

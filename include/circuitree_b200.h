@@ -86,6 +86,10 @@ int ct_engine_info(ct_engine *eng, int32_t *n_sm, int32_t *resident_lanes);
 int ct_compile_topology(int32_t n_species, const int64_t *act, int32_t n_act,
                         const int64_t *inh, int32_t n_inh, int32_t k, uint64_t *handle);
 
+/* Species (TFs) and reactions of a compiled topology (SPEC.md sections 2 and 9): the inputs of the
+ * per-step work I_step that bench.py's roofline uses (SPEC.md section 8). */
+int ct_topology_info(uint64_t handle, int32_t *n_species, int32_t *n_reactions);
+
 /*
  * Device-buffer launch.  Job j simulates n_traj[j] trajectories of topology handles[j]; its
  * trajectory ids are traj_base[j] .. traj_base[j]+n_traj[j]-1 and its outputs occupy the slots
@@ -170,6 +174,13 @@ const char *ct_tree_last_error(void);
  * max_interactions < 0 means n*n; n_exhausted = NaN means "never exhaust" (Python None). */
 int ct_tree_create(const char *components, const char *types, int32_t max_interactions, const char *root,
                    double exploration_constant, double n_exhausted, ct_tree **out);
+/* Same tree over DimersGrammar states (reference circuitree/models.py:524-939: get_actions :646-739, do_action
+ * :741-757, get_unique_state :759-826, parse_genotype :844-884), e.g. root "ABC+DE::"; components / regulators /
+ * types one character each in declaration order; at most 5 TFs in total.  ct_tree_key_to_handle registers the
+ * state with ct_compile_topology(k = 3).  Such trees do not support the replica exchange (process-local keys). */
+int ct_tree_create_dimers(const char *components, const char *regulators, const char *types, int32_t max_interactions,
+                          int32_t max_per_promoter, const char *root, double exploration_constant, double n_exhausted,
+                          ct_tree **out);
 int ct_tree_destroy(ct_tree *t);
 /* numpy Generator(PCG64).bit_generator.state: 128-bit state and inc as (lo, hi) words. */
 int ct_tree_set_rng(ct_tree *t, const uint64_t state[2], const uint64_t inc[2], int32_t has_uint32, uint32_t uinteger);

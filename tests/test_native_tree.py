@@ -10,7 +10,7 @@ import zlib
 import numpy as np
 import pytest
 
-from circuitree_b200 import CircuiTree, SimpleNetworkGrammar
+from circuitree_b200 import CircuiTree, DimersGrammar, SimpleNetworkGrammar
 from circuitree_b200.native import NativeExhaustionError, NativeTree
 
 AI = ["activates", "inhibits"]
@@ -302,3 +302,90 @@ def test_unsupported_configurations_are_refused():
         NativeTree(SimpleNetworkGrammar(list("ABCDEF"), AI), "ABCDEF::", seed=0, reward_fn=crc_rewards)
     with pytest.raises(_capi.EngineError):
         NativeTree(SimpleNetworkGrammar(list("ABC"), AI, fixed_components=["A"]), "ABC::", seed=0, reward_fn=crc_rewards)
+
+
+# ---- DimersGrammar on the native tree (reference models.py:524-939; parity target = the Python mirror, which is
+# pinned to the reference wherever the reference runs and restates its documented intent elsewhere) ----
+def dimers_grammar(comps="ABC", regs="DE", **kw):
+    return DimersGrammar(components=list(comps), regulators=list(regs), interactions=AI, **kw)
+
+
+def test_native_dimers_actions_and_canonical_forms_match_the_mirror():
+    for comps, regs, kw in (("ABC", "DE", {}), ("AB", "R", {}), ("ABCDE", "", {}), ("BCA", "ED", {"max_interactions_per_promoter": 1}),
+                            ("ABC", "R", {"max_interactions": 3})):
+        g = dimers_grammar(comps, regs, **kw)
+        root = "".join(sorted(comps)) + "+" + "".join(sorted(regs)) + "::"
+        t = NativeTree(g, root, seed=0, reward_fn=crc_rewards)
+        py = CrcTree(grammar=g, root=root, seed=5, n_exhausted=np.inf)
+        rg = np.random.default_rng(7)
+        state = root
+        seen = 0
+        for _ in range(400):
+            acts = g.get_actions(state)
+            assert t.get_actions(state) == acts, state
+            if not acts:
+                state = root
+                continue
+            state = py._do_action(state, acts[int(rg.integers(len(acts)))])
+            # a scrambled spelling of the same circuit canonicalises to the same string on both sides
+            body = [x for x in state.split("::")[1].split("_") if x]
+            if body:
+                cp = dict(zip(sorted(comps), rg.permutation(sorted(comps))))
+                rp = dict(zip(sorted(regs), rg.permutation(sorted(regs)))) if regs else {}
+                m = {**cp, **rp}
+                sc = ["".join(m.get(ch, ch) for ch in x) for x in body]
+                sc = [(x[1] + x[0] + x[2:]) if rg.random() < 0.5 else x for x in sc]
+                rg.shuffle(sc)
+                raw = ("*" if state.startswith("*") else "") + root + "_".join(sc)
+                assert t.get_unique_state(raw) == g.get_unique_state(raw), raw
+                seen += 1
+        assert seen > 100
+
+
+@pytest.mark.parametrize("comps,regs,steps,seed,n_exh,batch,depth", [
+    ("ABC", "DE", 600, 1, np.inf, 1, 1),
+    ("AB", "R", 1500, 2, np.inf, 1, 1),
+    ("ABC", "R", 800, 3, np.inf, 16, 2),
+    ("AB", "", 3000, 4, 3, 1, 1),
+    ("AB", "R", 4000, 5, 2, 8, 2),
+])
+def test_native_dimers_mcts_is_bit_exact_with_the_mirror(comps, regs, steps, seed, n_exh, batch, depth):
+    """Same leaves, same statistics, same RNG state as the Python tree on DimersGrammar states --
+    sequential, batched / pipelined, and with finite n_exhausted."""
+    from circuitree_b200 import ExhaustionError
+
+    g = dimers_grammar(comps, regs)
+    root = comps + "+" + regs + "::"
+    py = CrcTree(grammar=g, root=root, seed=seed, n_exhausted=n_exh)
+    nt = NativeTree(dimers_grammar(comps, regs), root, seed=seed, n_exhausted=n_exh, reward_fn=crc_rewards)
+    dp, dn, ep, en = [], [], None, None
+    try:
+        py.search_mcts_batched(steps, batch, pipeline_depth=depth, callback_before_start=False,
+                               callback=lambda t, i, p, s, r: dp.append(step_digest(p, s, r)))
+    except ExhaustionError:
+        ep = "ExhaustionError"
+    try:
+        nt.search_mcts(steps, batch_size=batch, pipeline_depth=depth, callback=lambda t, i, p, s, r: dn.append(step_digest(p, s, r)))
+    except NativeExhaustionError:
+        en = "ExhaustionError"
+    assert ep == en
+    assert dn == dp and len(dn) > 100
+    assert graph_digest(nt.to_networkx()) == graph_digest(py.graph)
+    if ep is None:
+        assert nt.rg.bit_generator.state == py.rg.bit_generator.state
+
+
+def test_native_dimers_handles_and_limits():
+    from circuitree_b200 import _capi
+
+    g = dimers_grammar("ABC", "DE")
+    t = NativeTree(g, "ABC+DE::", seed=0, reward_fn=crc_rewards)
+    for s in ["*ABC+DE::ADiB_BEiC_CCiA", "*ABC+DE::AAaA_ABiA_BDaC", "*ABC+DE::"]:
+        comps, regs, act, inh = g.parse_genotype(s)
+        assert t.handle_of_key(t.string_to_key(s, canonical=False)) == _capi.compile_topology(5, act, inh, k=3), s
+    with pytest.raises(_capi.EngineError):
+        NativeTree(dimers_grammar("ABCD", "EF"), "ABCD+EF::", seed=0, reward_fn=crc_rewards)       # six TFs
+    with pytest.raises(_capi.EngineError):
+        NativeTree(g, "AB+DE::", seed=0, reward_fn=crc_rewards)                                     # partial root
+    with pytest.raises(_capi.EngineError):
+        t.pack_deltas()                                                                             # process-local keys
