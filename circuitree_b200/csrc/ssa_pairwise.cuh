@@ -265,7 +265,8 @@ __device__ __forceinline__ void lane_park(Lane<MM>& L)
 template <int MM, bool kAllSpecies, bool kFast>
 __device__ __forceinline__ void ssa_step(Lane<MM>& L, bool& active, bool& finished, const uint32_t pres,
                                          const uint32_t actm, const int nsp_in, uint32_t w_tau, uint32_t w_sel,
-                                         uint8_t* ser, const int nt, const int decim, const float dt)
+                                         uint8_t* __restrict__ records, const uint32_t rec_off, const int nt, const int decim,
+                                         const float dt)
 {
     const int nsp = kAllSpecies ? MM : nsp_in;   // kAllSpecies: every job has MM species, no per-gene tests
     auto has = [&](int i, int j) -> bool { return (pres >> (i * kTopoStride + j)) & 1u; };
@@ -323,7 +324,7 @@ __device__ __forceinline__ void ssa_step(Lane<MM>& L, bool& active, bool& finish
 #pragma unroll
                 for (int j = 0; j < MM; ++j) {
                     CT_CHECK(L.kd >= 0 && L.kd < kSerStride);
-                    if (j < nsp) ser[j * kSerStride + L.kd] = (uint8_t)compand_block(L.blk[j]);
+                    if (j < nsp) records[rec_off + (uint32_t)(j * kSerStride + L.kd)] = (uint8_t)compand_block(L.blk[j]);
                     L.blk[j] = 0.0f;
                 }
                 L.kd += 1;
@@ -535,8 +536,14 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? CT_MINB3 : (MM == 4 ? CT_M
     float* z = reinterpret_cast<float*>(smem) + warp * kSerStride;
     uint8_t* stage = smem + (size_t)(kThreads / 32) * kSerStride * sizeof(float) + (size_t)warp * (MM * kSerStride);
     // this lane's record and the first record of its warp, in the global scratch area
-    uint8_t* warp_ser = A.records + ((size_t)blockIdx.x * kThreads + (size_t)warp * 32) * (MM * kSerStride);
-    uint8_t* ser = warp_ser + (size_t)lane * (MM * kSerStride);
+    // (a 32-bit offset the compiler cannot re-derive from the thread ids: otherwise it rebuilds the 64-bit address
+    // of the record -- two special-register reads and half a dozen integer operations -- in every step)
+    uint32_t rec_off;
+    {
+        const uint32_t v = (blockIdx.x * (uint32_t)kThreads + threadIdx.x) * (uint32_t)(MM * kSerStride);
+        asm volatile("mov.u32 %0, %1;" : "=r"(rec_off) : "r"(v));
+    }
+    const uint32_t warp_rec_off = rec_off - (uint32_t)lane * (uint32_t)(MM * kSerStride);
 
     static_assert(!kFast || (!kMixed && kAllSpecies), "kFast needs one full-size topology per warp");
     Lane<MM> L;
@@ -574,7 +581,7 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? CT_MINB3 : (MM == 4 ? CT_M
                 float rw; int lg;
                 const int nsp_src = kMixed ? (int)(__shfl_sync(kFull, pres, src) >> 28) : nsp;
                 // stage the record in shared memory (L2 reads: another lane wrote it), then reduce it
-                const uint32_t* grec = reinterpret_cast<const uint32_t*>(warp_ser + (size_t)src * (MM * kSerStride));
+                const uint32_t* grec = reinterpret_cast<const uint32_t*>(A.records + warp_rec_off + (uint32_t)src * (uint32_t)(MM * kSerStride));
                 for (int w = lane; w < nsp_src * (kSerStride / 4); w += 32) reinterpret_cast<uint32_t*>(stage)[w] = __ldcg(grec + w);
                 __syncwarp();
                 const uint8_t* sser = stage;
@@ -685,7 +692,7 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? CT_MINB3 : (MM == 4 ? CT_M
 #endif
         for (int h = 0; h < 2; ++h)
             ssa_step<MM, kAllSpecies, kFast>(L, active, finished, u_pres, u_act, u_nsp, h ? x.w[2] : x.w[0], h ? x.w[3] : x.w[1],
-                                      ser, A.nt, A.decim, A.dt);
+                                      A.records, rec_off, A.nt, A.decim, A.dt);
     }
     if (A.warp_iters && lane == 0) atomicAdd(A.warp_iters, n_iters);
 }
