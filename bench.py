@@ -355,8 +355,9 @@ def main() -> None:
                      "frac": achieved / peak, "traffic": None,
                      "note": f"algorithmic I_step(R=18, M=3) = {I_REP:.1f} issue slots/step (SPEC.md section 8) x steps/s per GPU; "
                              f"peak = {n_sm} SMs x 128 lanes x {sm_max:.0f} MHz (issue bound: no HBM or tensor roofline applies); "
-                             "DRAM traffic is not measurable inside this run: ncu puts one 2^22 launch at 71 MB read+written "
-                             f"(profiles/) against {(n * 12) / 1e6:.0f} MB of outputs + {(n * 4) / 1e6:.0f} MB launch order"},
+                             "DRAM traffic is not measurable inside this run (null): ncu puts one 2^20 launch at 46 MB read+written "
+                             "(profiles/r02_final_ssa_pairwise_M3_2p20.txt; outputs 12.6 MB + launch order 12.6 MB + the L2-resident "
+                             f"record scratch), i.e. ~0.06 TB/s against {(n * 12) / 1e6:.0f} MB of outputs per 2^{args.log2_traj} launch"},
         "mean_reward": mean_reward, "wall_s_timed_region": wall,
     }
 
