@@ -266,7 +266,7 @@ template <int MM, bool kAllSpecies, bool kFast>
 __device__ __forceinline__ void ssa_step(Lane<MM>& L, bool& active, bool& finished, const uint32_t pres,
                                          const uint32_t actm, const int nsp_in, uint32_t w_tau, uint32_t w_sel,
                                          uint8_t* __restrict__ records, const uint32_t rec_off, const int nt, const int decim,
-                                         const float dt)
+                                         const float dt, const int h)
 {
     const int nsp = kAllSpecies ? MM : nsp_in;   // kAllSpecies: every job has MM species, no per-gene tests
     auto has = [&](int i, int j) -> bool { return (pres >> (i * kTopoStride + j)) & 1u; };
@@ -313,7 +313,6 @@ __device__ __forceinline__ void ssa_step(Lane<MM>& L, bool& active, bool& finish
     const float tau = (-0.69314718056f * fast_log2(u01(w_tau))) * fast_rcp(a0);   // a0 == 0 -> +inf
     L.t_rem -= tau;
     bool alive = true;     // no early return: every lane must reach the warp votes below
-    const bool was_active = active;
     if (active && L.t_rem < 0.0f) {
         do {
 #pragma unroll
@@ -335,6 +334,9 @@ __device__ __forceinline__ void ssa_step(Lane<MM>& L, bool& active, bool& finish
             alive = false;
             active = false;
             finished = true;
+            // events fired = steps executed before this one (the crossing step fires nothing and is not counted,
+            // SPEC.md section 6): step h of Philox block ctr - 1 -- no per-step counter in the hot loop
+            L.events = 2u * (L.ctr - 1u) + (uint32_t)h;
         }
     }
 
@@ -395,7 +397,6 @@ __device__ __forceinline__ void ssa_step(Lane<MM>& L, bool& active, bool& finish
         }
         t -= g[j];
     }
-    L.events += (was_active && alive) ? 1u : 0u;
     if (!alive) lane_park<MM>(L);   // zero rates and state (rare; after the last use of the state above)
 }
 
@@ -692,7 +693,7 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? CT_MINB3 : (MM == 4 ? CT_M
 #endif
         for (int h = 0; h < 2; ++h)
             ssa_step<MM, kAllSpecies, kFast>(L, active, finished, u_pres, u_act, u_nsp, h ? x.w[2] : x.w[0], h ? x.w[3] : x.w[1],
-                                      A.records, rec_off, A.nt, A.decim, A.dt);
+                                      A.records, rec_off, A.nt, A.decim, A.dt, h);
     }
     if (A.warp_iters && lane == 0) atomicAdd(A.warp_iters, n_iters);
 }
