@@ -21,6 +21,9 @@
 // trajectories: rolled 1.495e11 steps/s, unrolled 1.572e11.  Tried and dropped: a predicated
 // (branch-free) first grid crossing (-3 %), generating the next Philox block beside the current
 // block's steps (+-0 %).
+#ifndef CT_BLOCKS_PER_CHECK
+#define CT_BLOCKS_PER_CHECK 4  // Philox blocks (two steps each) between two looks for idle lanes in the pairwise kernels
+#endif
 #ifndef CT_UNROLL_H
 #define CT_UNROLL_H 1         // 1: the two steps of a Philox block are unrolled into one basic block
 #endif
@@ -198,7 +201,7 @@ struct Lane {
     float blk[MM];
     float k_on, k_on2, k_off1, k_off2, km0, km1, km2, km3, kp, gm, gp;   // k_on2 = 2 k_on
     float t_rem;
-    int k, kd, dcount;
+    int kd, dcount;          // record block index; grid samples left in the block
     uint32_t events;
     uint32_t ctr;           // next Philox block of stream 1
     uint32_t traj_lo, traj_hi;
@@ -235,7 +238,7 @@ __device__ __forceinline__ void lane_park(Lane<MM>& L)
 #pragma unroll
         for (int i = 0; i < MM; ++i) L.b[i][j] = 0.0f;
     }
-    L.t_rem = 0.0f;
+    L.t_rem = __int_as_float(0x7f800000);   // +inf: never "crosses a grid point" (ssa_step)
 }
 
 // One SSA step (SPEC.md section 2) executed by ALL lanes of the warp in lock-step; lanes without a
@@ -266,7 +269,7 @@ template <int MM, bool kAllSpecies, bool kFast>
 __device__ __forceinline__ void ssa_step(Lane<MM>& L, bool& active, bool& finished, const uint32_t pres,
                                          const uint32_t actm, const int nsp_in, uint32_t w_tau, uint32_t w_sel,
                                          uint8_t* __restrict__ records, const uint32_t rec_off, const int nt, const int decim,
-                                         const float dt, const int h)
+                                         const int n_dec, const float dt, const int h)
 {
     const int nsp = kAllSpecies ? MM : nsp_in;   // kAllSpecies: every job has MM species, no per-gene tests
     auto has = [&](int i, int j) -> bool { return (pres >> (i * kTopoStride + j)) & 1u; };
@@ -310,44 +313,55 @@ __device__ __forceinline__ void ssa_step(Lane<MM>& L, bool& active, bool& finish
     for (int j = 1; j < MM; ++j) a0 += g[j];
 
     // ---- time to next event; grid samples crossed keep the pre-event state ----
+    // A lane without a trajectory carries t_rem = +inf and a0 = 0: tau = +inf, t_rem turns NaN and stays NaN, so
+    // "t_rem < 0" is false for it without a test of `active`.  (u01 is never 1, so tau of a live lane is never NaN.)
     const float tau = (-0.69314718056f * fast_log2(u01(w_tau))) * fast_rcp(a0);   // a0 == 0 -> +inf
     L.t_rem -= tau;
-    bool alive = true;     // no early return: every lane must reach the warp votes below
-    if (active && L.t_rem < 0.0f) {
+    float t = u01(w_sel) * a0;      // selection target (a lane that finishes below fires nothing: target beyond every sum)
+    // No early return: every lane must reach the warp votes below.  In a 32-lane warp some lane crosses a grid point
+    // in four steps out of ten, nearly always alone, so this divergent path is part of the hot loop and kept short:
+    // the grid index is not counted per sample, only per record block (k = kd * decim + decim - dcount), and the end
+    // of the trajectory can only be met at a block boundary.
+    if (L.t_rem < 0.0f) {
         do {
 #pragma unroll
             for (int j = 0; j < MM; ++j) L.blk[j] += fminf(L.P[j], kSampleCap);
-            L.k += 1;
             if (--L.dcount == 0) {
-                L.dcount = decim;
+                // block boundary: record (a trailing block shorter than `decim` is simulated but not recorded)
+                if (L.kd < n_dec) {
 #pragma unroll
-                for (int j = 0; j < MM; ++j) {
-                    CT_CHECK(L.kd >= 0 && L.kd < kSerStride);
-                    if (j < nsp) records[rec_off + (uint32_t)(j * kSerStride + L.kd)] = (uint8_t)compand_block(L.blk[j]);
-                    L.blk[j] = 0.0f;
+                    for (int j = 0; j < MM; ++j) {
+                        CT_CHECK(L.kd >= 0 && L.kd < kSerStride);
+                        if (j < nsp) records[rec_off + (uint32_t)(j * kSerStride + L.kd)] = (uint8_t)compand_block(L.blk[j]);
+                    }
                 }
+#pragma unroll
+                for (int j = 0; j < MM; ++j) L.blk[j] = 0.0f;
                 L.kd += 1;
+                const int left = nt - L.kd * decim;        // grid points after this boundary
+                if (left <= 0) {
+                    // last grid sample taken: the lane parks until the warp reduces its record.
+                    // events fired = steps executed before this one (the crossing step fires nothing and is not
+                    // counted, SPEC.md section 6): step h of Philox block ctr - 1 -- no per-step counter in the hot loop
+                    L.events = 2u * (L.ctr - 1u) + (uint32_t)h;
+                    active = false;
+                    finished = true;
+                    t = 3.0e38f;
+                    lane_park<MM>(L);   // zero rates and state: the updates below add zeros to it
+                    break;
+                }
+                L.dcount = min(decim, left);
             }
             L.t_rem += dt;
-        } while (L.t_rem < 0.0f && L.k < nt);
-        if (L.k >= nt) {           // last grid sample recorded: the lane parks until the warp reduces its record
-            alive = false;
-            active = false;
-            finished = true;
-            // events fired = steps executed before this one (the crossing step fires nothing and is not counted,
-            // SPEC.md section 6): step h of Philox block ctr - 1 -- no per-step counter in the hot loop
-            L.events = 2u * (L.ctr - 1u) + (uint32_t)h;
-        }
+        } while (L.t_rem < 0.0f);
     }
 
-
-    // ---- select and fire (a lane that has just finished fires nothing: target beyond every sum) ----
+    // ---- select and fire ----
     // s_r = [t < lc_r] as a float comes from the FMA pipe: saturate((lc_r - t) * 2^60) is 1 when
     // lc_r > t (the smallest positive difference of two such floats is far above 2^-60) and 0 when
     // lc_r <= t; the scaling by a power of two is exact, so the sign is that of the exact difference.
     // The compare/select pipe runs at half the FMA pipe's rate and is the busier one in this loop.
     constexpr float kBig = 1152921504606846976.0f;   // 2^60
-    float t = alive ? u01(w_sel) * a0 : 3.0e38f;
     float s_prev = 0.0f;
 #pragma unroll
     for (int j = 0; j < MM; ++j) {
@@ -397,7 +411,6 @@ __device__ __forceinline__ void ssa_step(Lane<MM>& L, bool& active, bool& finish
         }
         t -= g[j];
     }
-    if (!alive) lane_park<MM>(L);   // zero rates and state (rare; after the last use of the state above)
 }
 
 // Parameter vector of one trajectory (SPEC.md sections 3-4): explicit if given, else sampled.
@@ -517,7 +530,7 @@ __device__ __forceinline__ void lane_init(Lane<MM>& L, const LaunchArgs& A, cons
         L.kmb[j] = act ? L.km1 : L.km2;
     }
     L.t_rem = 0.0f;
-    L.k = 0; L.kd = 0; L.dcount = A.decim;
+    L.kd = 0; L.dcount = A.decim;
     L.events = 0;
     L.ctr = 0;
 }
@@ -553,7 +566,7 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? CT_MINB3 : (MM == 4 ? CT_M
     for (int j = 0; j < MM; ++j)
 #pragma unroll
         for (int i = 0; i < MM; ++i) L.h[i][j] = 0.0f;
-    L.k = 0; L.kd = 0; L.dcount = 1; L.events = 0; L.ctr = 0; L.traj_lo = L.traj_hi = 0; L.out = 0;
+    L.kd = 0; L.dcount = 1; L.events = 0; L.ctr = 0; L.traj_lo = L.traj_hi = 0; L.out = 0;
     bool active = false, finished = false;
     // topology as two 25-bit masks + species count in bits 28..31 of `pres`
     // (uniform mode: the warp's topology; mixed mode: this lane's topology)
@@ -675,25 +688,30 @@ __global__ void __launch_bounds__(kThreads, MM <= 3 ? CT_MINB3 : (MM == 4 ? CT_M
             }
             if (out_of_work && __ballot_sync(kFull, active) == 0u) break;
         }
-        ++n_iters;
+        n_iters += CT_BLOCKS_PER_CHECK;
 
-        // two steps per Philox block (SPEC.md section 3); every lane runs them, parked lanes as no-ops
-        const Philox4 x = philox4x32_10_rk(L.ctr, 1u, L.traj_lo, L.traj_hi, A.rk);
-        L.ctr += 1;
         // A warp-wide OR of identical values: the result is warp-uniform by construction, which lets
         // the compiler keep the topology in uniform registers and branch uniformly on its bits.
         // (kFast reads the per-lane 0/1 edge matrix instead: no topology bits in its hot loop)
         const uint32_t u_pres = (kMixed || kFast) ? pres : __reduce_or_sync(kFull, pres);
         const uint32_t u_act = (kMixed || kFast) ? actm : __reduce_or_sync(kFull, actm);
         const int u_nsp = (int)(u_pres >> 28);
+        // CT_BLOCKS_PER_CHECK Philox blocks between two looks for idle lanes (the vote, its convergence check and
+        // the branch are 8 instructions); two steps per block (SPEC.md section 3); every lane runs them, parked
+        // lanes as no-ops, so a lane that finishes waits at most that many blocks for its reduction and refill.
+#pragma unroll 1
+        for (int rep = 0; rep < CT_BLOCKS_PER_CHECK; ++rep) {
+            const Philox4 x = philox4x32_10_rk(L.ctr, 1u, L.traj_lo, L.traj_hi, A.rk);
+            L.ctr += 1;
 #if CT_UNROLL_H
 #pragma unroll
 #else
 #pragma unroll 1
 #endif
-        for (int h = 0; h < 2; ++h)
-            ssa_step<MM, kAllSpecies, kFast>(L, active, finished, u_pres, u_act, u_nsp, h ? x.w[2] : x.w[0], h ? x.w[3] : x.w[1],
-                                      A.records, rec_off, A.nt, A.decim, A.dt, h);
+            for (int h = 0; h < 2; ++h)
+                ssa_step<MM, kAllSpecies, kFast>(L, active, finished, u_pres, u_act, u_nsp, h ? x.w[2] : x.w[0], h ? x.w[3] : x.w[1],
+                                          A.records, rec_off, A.nt, A.decim, A.n_dec, A.dt, h);
+        }
     }
     if (A.warp_iters && lane == 0) atomicAdd(A.warp_iters, n_iters);
 }
