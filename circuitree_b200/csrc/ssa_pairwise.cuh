@@ -22,7 +22,7 @@
 // (branch-free) first grid crossing (-3 %), generating the next Philox block beside the current
 // block's steps (+-0 %).
 #ifndef CT_BLOCKS_PER_CHECK
-#define CT_BLOCKS_PER_CHECK 4  // Philox blocks (two steps each) between two looks for idle lanes in the pairwise kernels
+#define CT_BLOCKS_PER_CHECK 8  // Philox blocks (two steps each) between two looks for idle lanes in the pairwise kernels
 #endif
 #ifndef CT_UNROLL_H
 #define CT_UNROLL_H 1         // 1: the two steps of a Philox block are unrolled into one basic block
