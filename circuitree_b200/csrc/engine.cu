@@ -201,7 +201,12 @@ int ct_engine_create(int device, ct_engine** out)
     }
     if (device < 0 || device >= n_dev) return fail(CT_ERR_INVALID, "device %d out of range [0,%d)", device, n_dev);
     CT_CUDA(cudaSetDevice(device));
-    ct_engine* eng = new ct_engine();
+    // (owned by the guard until the last step has succeeded: every early return below destroys stream and engine)
+    struct EngineGuard {
+        ct_engine* e;
+        ~EngineGuard() { if (e) ct_engine_destroy(e); }
+    } guard{new ct_engine()};
+    ct_engine* eng = guard.e;
     eng->device = device;
     cudaDeviceProp prop;
     CT_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -221,14 +226,14 @@ int ct_engine_create(int device, ct_engine** out)
     }
     int rc;
 #define CT_PREP(MM, MIXED, ALL) \
-    if ((rc = prepare_kernel<MM, MIXED, ALL>(eng->ki[MM - 3][MIXED][ALL])) != CT_OK) { delete eng; return rc; }
+    if ((rc = prepare_kernel<MM, MIXED, ALL>(eng->ki[MM - 3][MIXED][ALL])) != CT_OK) return rc;
     CT_PREP(3, false, false) CT_PREP(3, false, true) CT_PREP(3, true, false) CT_PREP(3, true, true)
     CT_PREP(4, false, false) CT_PREP(4, false, true) CT_PREP(4, true, false) CT_PREP(4, true, true)
     CT_PREP(5, false, false) CT_PREP(5, false, true) CT_PREP(5, true, false) CT_PREP(5, true, true)
 #undef CT_PREP
-    if ((rc = prepare_kernel<3, false, true, true>(eng->ki_fast[0])) != CT_OK) { delete eng; return rc; }
-    if ((rc = prepare_kernel<4, false, true, true>(eng->ki_fast[1])) != CT_OK) { delete eng; return rc; }
-    if ((rc = prepare_kernel<5, false, true, true>(eng->ki_fast[2])) != CT_OK) { delete eng; return rc; }
+    if ((rc = prepare_kernel<3, false, true, true>(eng->ki_fast[0])) != CT_OK) return rc;
+    if ((rc = prepare_kernel<4, false, true, true>(eng->ki_fast[1])) != CT_OK) return rc;
+    if ((rc = prepare_kernel<5, false, true, true>(eng->ki_fast[2])) != CT_OK) return rc;
     {
         // the dimer kernel sizes its shared memory per launch (DimerLayout); allow the maximum here
         KernelInfo& ki = eng->ki_dimers;
@@ -252,11 +257,10 @@ int ct_engine_create(int device, ct_engine** out)
             cudaFuncSetAttribute(ct::ssa_dimers_coop_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
             e1 = cudaErrorUnknown;
         if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess ||
-            ki.blocks_per_sm < 1) {
-            delete eng;
+            ki.blocks_per_sm < 1)
             return fail(CT_ERR_CUDA, "dimer SSA kernel does not fit on an SM");
-        }
     }
+    guard.e = nullptr;
     *out = eng;
     return CT_OK;
 }
@@ -851,18 +855,18 @@ int ct_reward_from_series_host(ct_engine* eng, const uint8_t* h_series, int32_t 
     uint8_t* d_series = nullptr;
     float* d_reward = nullptr;
     int32_t* d_lag = nullptr;
-    CT_CUDA(cudaMallocAsync((void**)&d_series, bytes, s));
-    CT_CUDA(cudaMallocAsync((void**)&d_reward, sizeof(float) * n, s));
-    CT_CUDA(cudaMallocAsync((void**)&d_lag, sizeof(int32_t) * n, s));
-    CT_CUDA(cudaMemcpyAsync(d_series, h_series, bytes, cudaMemcpyHostToDevice, s));
-    ct::reward_from_series_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_series, n, n_species, n_dec, d_reward, d_lag);
-    CT_CUDA(cudaGetLastError());
-    eng->launches += 1;
-    CT_CUDA(cudaMemcpyAsync(h_reward, d_reward, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
-    CT_CUDA(cudaMemcpyAsync(h_lag, d_lag, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
-    cudaFreeAsync(d_series, s);
-    cudaFreeAsync(d_reward, s);
-    cudaFreeAsync(d_lag, s);
+    {
+        StreamScratch scratch(s);       // freed in stream order at the end of this block, on every path
+        CT_CUDA(scratch.alloc(&d_series, bytes));
+        CT_CUDA(scratch.alloc(&d_reward, sizeof(float) * n));
+        CT_CUDA(scratch.alloc(&d_lag, sizeof(int32_t) * n));
+        CT_CUDA(cudaMemcpyAsync(d_series, h_series, bytes, cudaMemcpyHostToDevice, s));
+        ct::reward_from_series_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_series, n, n_species, n_dec, d_reward, d_lag);
+        CT_CUDA(cudaGetLastError());
+        eng->launches += 1;
+        CT_CUDA(cudaMemcpyAsync(h_reward, d_reward, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
+        CT_CUDA(cudaMemcpyAsync(h_lag, d_lag, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+    }
     CT_CUDA(cudaStreamSynchronize(s));
     return CT_OK;
 }
