@@ -97,3 +97,21 @@ def test_product_never_imports_oracle():
         assert "oracle" not in src.replace("no oracle", ""), f"{path} mentions the oracle"
     for path in (ROOT / "circuitree_b200" / "csrc").glob("*"):
         assert "oracle" not in path.read_text(), path
+
+
+def test_fast_loop_instruction_budget():
+    """The headline kernel is bound by instruction issue: its roofline fraction is
+    I_step / (instructions executed per step) x issue efficiency, so the instruction count of the main path of the
+    built library is part of the contract.  Static count from the SASS (scripts/sass_hot_loop.py,
+    profiles/r02_final_fast_loop_sass.txt): 280 per Philox block = 140 per step against I_step = 113.5."""
+    import shutil
+    import subprocess
+    import sys
+
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    out = subprocess.run([sys.executable, str(ROOT / "scripts" / "sass_hot_loop.py")], capture_output=True, text=True, check=True).stdout
+    head = out.splitlines()[1]
+    n = int(head.split("point): ")[1].split()[0])
+    assert 227 <= n <= 290, head          # 227 = 2 x I_step: fewer would mean the walk lost the path
+    assert "MUFU 4" in out.splitlines()[3] and "IMAD 21" in out.splitlines()[3]      # 2 x (lg2 + rcp), Philox + 1
