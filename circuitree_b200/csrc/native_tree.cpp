@@ -300,6 +300,50 @@ struct DimerSpace {
         return ct_compile_topology(S, act.data(), (int32_t)(act.size() / 3), inh.data(), (int32_t)(inh.size() / 3), 3, handle) == CT_OK;
     }
     int depth_of(uint64_t key) const { return (int)lists[(size_t)(key & 0xffffffffull)].size() + ((key & kTerminalBit) ? 1 : 0); }
+
+    // Keys are process-local ids of interned lists, so replicas exchange the lists themselves: a state travels as
+    // wire_words() 64-bit words -- word 0: terminal flag (bit 0), list length (bits 1..7), codes 0..5 (9 bits each from
+    // bit 8); every further word: seven more codes from bit 0.  Every replica of a search builds the same code table
+    // (same components, regulators and types), and node keys are canonical lists, so the codes mean the same everywhere.
+    int max_list_len() const
+    {
+        const int by_promoter = max_per_promoter * C;
+        return max_interactions < by_promoter ? max_interactions : by_promoter;
+    }
+    int wire_words() const
+    {
+        const int cap = max_list_len();
+        return 1 + (cap > 6 ? (cap - 6 + 6) / 7 : 0);
+    }
+    bool to_wire(uint64_t key, int64_t* w) const
+    {
+        const std::vector<uint16_t>& v = lists[(size_t)(key & 0xffffffffull)];
+        const int W = wire_words();
+        if ((int)v.size() > 6 + 7 * (W - 1) || v.size() > 127) return false;
+        for (int x = 0; x < W; ++x) w[x] = 0;
+        uint64_t w0 = ((key & kTerminalBit) ? 1ull : 0ull) | ((uint64_t)v.size() << 1);
+        for (size_t x = 0; x < v.size(); ++x) {
+            if (v[x] >= 512) return false;
+            if (x < 6) w0 |= (uint64_t)v[x] << (8 + 9 * x);
+            else w[1 + (x - 6) / 7] |= (int64_t)((uint64_t)v[x] << (9 * ((x - 6) % 7)));
+        }
+        w[0] = (int64_t)w0;
+        return true;
+    }
+    bool from_wire(const int64_t* w, uint64_t* key)
+    {
+        const uint64_t w0 = (uint64_t)w[0];
+        const size_t n = (size_t)((w0 >> 1) & 127u);
+        if ((int)n > 6 + 7 * (wire_words() - 1)) return false;
+        std::vector<uint16_t> v(n);
+        const int n_codes = S * S * T * S;
+        for (size_t x = 0; x < n; ++x) {
+            v[x] = (uint16_t)(x < 6 ? (w0 >> (8 + 9 * x)) & 511u : ((uint64_t)w[1 + (x - 6) / 7] >> (9 * ((x - 6) % 7))) & 511u);
+            if (v[x] >= n_codes || (x && v[x] <= v[x - 1])) return false;      // a sorted list of distinct valid codes
+        }
+        *key = ((w0 & 1u) ? kTerminalBit : 0ull) | intern(v);
+        return true;
+    }
 };
 
 }  // namespace
@@ -942,25 +986,27 @@ int ct_tree_grow(ct_tree* t)
 
 /* Multi-GPU root-parallel merge, step 1: everything this replica has to tell the others since the
  * previous successful call, as ONE buffer of 64-bit words:
- *   [0] kPackMagic  [1] n_node  [2] n_edge  [3] n_exhausted  [4] flags (bit 0: whole tree exhausted)
+ *   [0] kPackMagic  [1] n_node  [2] n_edge  [3] n_exhausted  [4] flags (bit 0: whole tree exhausted; bits 8..: words per key W)
  *   node keys[n_node] | node d visits[n_node] | node d reward[n_node] (double bits)
  *   edge parent keys[n_edge] | edge child keys[n_edge] | edge d visits[n_edge] | edge d reward[n_edge]
  *   keys of nodes flagged exhausted[n_exhausted]
+ * A key is one word (the packed state) for SimpleNetworkGrammar trees and W = flags >> 8 words for DimersGrammar
+ * trees, whose keys are process-local: the interaction list itself travels (DimerSpace::to_wire).
  * Records are sparse (only what changed) and keyed by packed state: 5-component spaces cannot be
  * indexed densely.  max_depth >= 0 restricts the exchange to states with at most that many
  * interactions (+1 for terminal states); -1 exchanges everything.  If buf is NULL or cap is too
  * small nothing is committed and *n_words is the size needed.  The statistics un-counted by
  * exhaustion (reference circuitree.py:386-420) never travel as increments: the exhaustion event does,
  * and every replica replays it (see settle_exhausted). */
-constexpr int64_t kPackMagic = 0x4354444c54413032ll;   // "CTDLTA02"
+constexpr int64_t kPackMagic = 0x4354444c54413033ll;   // "CTDLTA03"
 constexpr int64_t kPackHeader = 5;
 
 int ct_tree_pack_deltas(ct_tree* t, int32_t max_depth, int64_t* buf, int64_t cap, int64_t* n_words)
 {
     NvtxRange nvtx_range("ct_tree_pack_deltas");
     if (!t || !n_words) return tfail(CT_ERR_INVALID, "NULL argument");
-    if (t->dim) return tfail(CT_ERR_UNSUPPORTED, "DimersGrammar trees cannot be exchanged between replicas: their keys are process-local ids");
     if (t->track_exhaustion) t->settle_exhausted();
+    const int64_t W = t->dim ? t->dim->wire_words() : 1;
     auto wanted = [&](uint64_t key) { return max_depth < 0 || t->depth_of(key) <= max_depth; };
     int64_t nn = 0, ne = 0;
     for (const auto& nd : t->nodes)
@@ -968,29 +1014,48 @@ int ct_tree_pack_deltas(ct_tree* t, int32_t max_depth, int64_t* buf, int64_t cap
     for (const auto& e : t->edges)
         if ((e.visits != e.sync_visits || e.reward != e.sync_reward) && wanted(t->nodes[e.child].key)) ++ne;
     const int64_t nx = (int64_t)t->newly_exhausted.size();
-    const int64_t need = kPackHeader + 3 * nn + 4 * ne + nx;
+    const int64_t need = kPackHeader + (W + 2) * nn + (2 * W + 2) * ne + W * nx;
     *n_words = need;
     if (!buf || cap < need) return CT_OK;
-    buf[0] = kPackMagic; buf[1] = nn; buf[2] = ne; buf[3] = nx; buf[4] = t->exhausted_all ? 1 : 0;
-    int64_t* nk = buf + kPackHeader; int64_t* nv = nk + nn; int64_t* nr = nv + nn;
-    int64_t* ep = nr + nn; int64_t* ec = ep + ne; int64_t* ev = ec + ne; int64_t* er = ev + ne; int64_t* xk = er + ne;
+    auto put_key = [&](uint64_t key, int64_t* dst) -> bool {
+        if (!t->dim) { *dst = (int64_t)key; return true; }
+        return t->dim->to_wire(key, dst);
+    };
+    int64_t* nk = buf + kPackHeader; int64_t* nv = nk + W * nn; int64_t* nr = nv + nn;
+    int64_t* ep = nr + nn; int64_t* ec = ep + W * ne; int64_t* ev = ec + W * ne; int64_t* er = ev + ne; int64_t* xk = er + ne;
+    // keys first: nothing is committed (no sync baseline moves) if a state does not fit the wire format
+    {
+        int64_t a = 0, b = 0;
+        bool ok = true;
+        for (const auto& nd : t->nodes) {
+            if ((nd.visits == nd.sync_visits && nd.reward == nd.sync_reward) || !wanted(nd.key)) continue;
+            ok = put_key(nd.key, nk + W * a) && ok;
+            ++a;
+        }
+        for (const auto& e : t->edges) {
+            if ((e.visits == e.sync_visits && e.reward == e.sync_reward) || !wanted(t->nodes[e.child].key)) continue;
+            ok = put_key(t->nodes[e.parent].key, ep + W * b) && put_key(t->nodes[e.child].key, ec + W * b) && ok;
+            ++b;
+        }
+        for (int64_t x = 0; x < nx; ++x) ok = put_key(t->newly_exhausted[(size_t)x], xk + W * x) && ok;
+        if (!ok) return tfail(CT_ERR_UNSUPPORTED, "a state has more interactions than the exchange format of this grammar holds");
+    }
+    buf[0] = kPackMagic; buf[1] = nn; buf[2] = ne; buf[3] = nx; buf[4] = (t->exhausted_all ? 1 : 0) | (W << 8);
     int64_t a = 0, b = 0;
     for (auto& nd : t->nodes) {
         if ((nd.visits == nd.sync_visits && nd.reward == nd.sync_reward) || !wanted(nd.key)) continue;
         const double dr = nd.reward - nd.sync_reward;
-        nk[a] = (int64_t)nd.key; nv[a] = nd.visits - nd.sync_visits; memcpy(&nr[a], &dr, 8);
+        nv[a] = nd.visits - nd.sync_visits; memcpy(&nr[a], &dr, 8);
         nd.sync_visits = nd.visits; nd.sync_reward = nd.reward;
         ++a;
     }
     for (auto& e : t->edges) {
         if ((e.visits == e.sync_visits && e.reward == e.sync_reward) || !wanted(t->nodes[e.child].key)) continue;
         const double dr = e.reward - e.sync_reward;
-        ep[b] = (int64_t)t->nodes[e.parent].key; ec[b] = (int64_t)t->nodes[e.child].key;
         ev[b] = e.visits - e.sync_visits; memcpy(&er[b], &dr, 8);
         e.sync_visits = e.visits; e.sync_reward = e.reward;
         ++b;
     }
-    for (int64_t x = 0; x < nx; ++x) xk[x] = (int64_t)t->newly_exhausted[(size_t)x];
     t->newly_exhausted.clear();
     return CT_OK;
 }
@@ -1002,26 +1067,42 @@ int ct_tree_merge_packed(ct_tree* t, const int64_t* buf, int64_t n_words, int32_
 {
     NvtxRange nvtx_range("ct_tree_merge_packed");
     if (!t || !buf) return tfail(CT_ERR_INVALID, "NULL argument");
-    if (t->dim) return tfail(CT_ERR_UNSUPPORTED, "DimersGrammar trees cannot be exchanged between replicas: their keys are process-local ids");
     if (n_words < kPackHeader || buf[0] != kPackMagic) return tfail(CT_ERR_INVALID, "not a delta buffer");
     const int64_t nn = buf[1], ne = buf[2], nx = buf[3];
-    if (nn < 0 || ne < 0 || nx < 0 || kPackHeader + 3 * nn + 4 * ne + nx > n_words)
+    const int64_t W = t->dim ? t->dim->wire_words() : 1;
+    if ((buf[4] >> 8) != W) return tfail(CT_ERR_INVALID, "delta buffer of another grammar (%lld words per key, this tree uses %lld)",
+                                        (long long)(buf[4] >> 8), (long long)W);
+    if (nn < 0 || ne < 0 || nx < 0 || kPackHeader + (W + 2) * nn + (2 * W + 2) * ne + W * nx > n_words)
         return tfail(CT_ERR_INVALID, "truncated delta buffer");
-    const int64_t* nk = buf + kPackHeader; const int64_t* nv = nk + nn; const int64_t* nr = nv + nn;
-    const int64_t* ep = nr + nn; const int64_t* ec = ep + ne; const int64_t* ev = ec + ne; const int64_t* er = ev + ne;
+    const int64_t* nk = buf + kPackHeader; const int64_t* nv = nk + W * nn; const int64_t* nr = nv + nn;
+    const int64_t* ep = nr + nn; const int64_t* ec = ep + W * ne; const int64_t* ev = ec + W * ne; const int64_t* er = ev + ne;
     const int64_t* xk = er + ne;
+    auto get_key = [&](const int64_t* src, uint64_t* key) -> bool {
+        if (!t->dim) { *key = (uint64_t)*src; return true; }
+        return t->dim->from_wire(src, key);
+    };
+    // decode every key before touching the tree: a malformed buffer changes nothing
+    std::vector<uint64_t> keys((size_t)(nn + 2 * ne + nx));
+    for (int64_t x = 0; x < nn; ++x)
+        if (!get_key(nk + W * x, &keys[(size_t)x])) return tfail(CT_ERR_INVALID, "malformed state in a delta buffer");
+    for (int64_t x = 0; x < ne; ++x)
+        if (!get_key(ep + W * x, &keys[(size_t)(nn + 2 * x)]) || !get_key(ec + W * x, &keys[(size_t)(nn + 2 * x + 1)]))
+            return tfail(CT_ERR_INVALID, "malformed state in a delta buffer");
+    for (int64_t x = 0; x < nx; ++x)
+        if (!get_key(xk + W * x, &keys[(size_t)(nn + 2 * ne + x)])) return tfail(CT_ERR_INVALID, "malformed state in a delta buffer");
     for (int64_t x = 0; x < nn; ++x) {
-        int id = t->node_of((uint64_t)nk[x]);
-        if (id < 0) id = t->add_node((uint64_t)nk[x]);
+        int id = t->node_of(keys[(size_t)x]);
+        if (id < 0) id = t->add_node(keys[(size_t)x]);
         double dr; memcpy(&dr, &nr[x], 8);
         Node& nd = t->nodes[id];
         nd.visits += nv[x]; nd.reward += dr;
         nd.sync_visits += nv[x]; nd.sync_reward += dr;
     }
     for (int64_t x = 0; x < ne; ++x) {
-        int p = t->node_of((uint64_t)ep[x]), c = t->node_of((uint64_t)ec[x]);
-        if (p < 0) p = t->add_node((uint64_t)ep[x]);
-        if (c < 0) c = t->add_node((uint64_t)ec[x]);
+        const uint64_t pk = keys[(size_t)(nn + 2 * x)], ck = keys[(size_t)(nn + 2 * x + 1)];
+        int p = t->node_of(pk), c = t->node_of(ck);
+        if (p < 0) p = t->add_node(pk);
+        if (c < 0) c = t->add_node(ck);
         int e = t->edge_of(p, c);
         if (e < 0) e = t->add_edge(p, c);
         double dr; memcpy(&dr, &er[x], 8);
@@ -1031,7 +1112,7 @@ int ct_tree_merge_packed(ct_tree* t, const int64_t* buf, int64_t n_words, int32_
     }
     if (t->track_exhaustion) {
         for (int64_t x = 0; x < nx; ++x) {
-            const int id = t->node_of((uint64_t)xk[x]);
+            const int id = t->node_of(keys[(size_t)(nn + 2 * ne + x)]);
             if (id < 0 || t->nodes[id].exhausted) continue;    // (unknown: filtered out by max_depth)
             t->mark_exhausted(id, false);
         }

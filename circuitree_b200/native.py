@@ -332,14 +332,18 @@ class NativeTree:
 
     @staticmethod
     def unpack_deltas(buf: np.ndarray) -> dict:
-        """Readable view of a packed buffer (tests, diagnostics)."""
+        """Readable view of a packed buffer (tests, diagnostics).  Keys are one word per state for
+        SimpleNetworkGrammar trees (the packed state) and ``key_words`` words for DimersGrammar trees (the
+        interaction list itself: their keys are process-local); key arrays then have shape (n, key_words)."""
         nn, ne, nx = int(buf[1]), int(buf[2]), int(buf[3])
-        o, out = NativeTree.PACK_HEADER, {"tree_exhausted": bool(buf[4] & 1)}
-        for name, n, dt in (("node_key", nn, np.uint64), ("node_dv", nn, np.int64), ("node_dr", nn, np.float64),
-                            ("edge_pkey", ne, np.uint64), ("edge_ckey", ne, np.uint64), ("edge_dv", ne, np.int64),
-                            ("edge_dr", ne, np.float64), ("exhausted", nx, np.uint64)):
-            out[name] = buf[o: o + n].view(dt)
-            o += n
+        w = int(buf[4]) >> 8
+        o, out = NativeTree.PACK_HEADER, {"tree_exhausted": bool(buf[4] & 1), "key_words": w}
+        for name, n, dt, width in (("node_key", nn, np.uint64, w), ("node_dv", nn, np.int64, 1), ("node_dr", nn, np.float64, 1),
+                                   ("edge_pkey", ne, np.uint64, w), ("edge_ckey", ne, np.uint64, w), ("edge_dv", ne, np.int64, 1),
+                                   ("edge_dr", ne, np.float64, 1), ("exhausted", nx, np.uint64, w)):
+            a = buf[o: o + n * width].view(dt)
+            out[name] = a if width == 1 else a.reshape(n, width)
+            o += n * width
         return out
 
     # dict-style aliases of the two calls above

@@ -177,7 +177,8 @@ int ct_tree_create(const char *components, const char *types, int32_t max_intera
 /* Same tree over DimersGrammar states (reference circuitree/models.py:524-939: get_actions :646-739, do_action
  * :741-757, get_unique_state :759-826, parse_genotype :844-884), e.g. root "ABC+DE::"; components / regulators /
  * types one character each in declaration order; at most 5 TFs in total.  ct_tree_key_to_handle registers the
- * state with ct_compile_topology(k = 3).  Such trees do not support the replica exchange (process-local keys). */
+ * state with ct_compile_topology(k = 3).  Their node keys are process-local ids of interned interaction lists; the replica exchange below
+ * sends the lists themselves. */
 int ct_tree_create_dimers(const char *components, const char *regulators, const char *types, int32_t max_interactions,
                           int32_t max_per_promoter, const char *root, double exploration_constant, double n_exhausted,
                           ct_tree **out);
@@ -207,7 +208,8 @@ int ct_tree_grow(ct_tree *t);
  * nodes and edges plus the keys of nodes it flagged exhausted (circuitree.py:386-420) -- into one
  * buffer of 64-bit words (layout: csrc/native_tree.cpp); with buf == NULL or cap too small it only
  * reports the size needed.  max_depth >= 0 limits the exchange to states with at most that many
- * interactions.  merge adds another replica's buffer and replays its exhaustion events. */
+ * interactions.  merge adds another replica's buffer and replays its exhaustion events; a buffer of a tree
+ * with another key width (another grammar) or with a malformed state is refused and changes nothing. */
 int ct_tree_pack_deltas(ct_tree *t, int32_t max_depth, int64_t *buf, int64_t cap, int64_t *n_words);
 int ct_tree_merge_packed(ct_tree *t, const int64_t *buf, int64_t n_words, int32_t *tree_exhausted);
 

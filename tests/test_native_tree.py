@@ -387,5 +387,98 @@ def test_native_dimers_handles_and_limits():
         NativeTree(dimers_grammar("ABCD", "EF"), "ABCD+EF::", seed=0, reward_fn=crc_rewards)       # six TFs
     with pytest.raises(_capi.EngineError):
         NativeTree(g, "AB+DE::", seed=0, reward_fn=crc_rewards)                                     # partial root
+
+
+def _node_stats(tree):
+    g = tree.to_networkx()
+    return ({n: (d["visits"], round(d["reward"], 9), bool(d.get("is_exhausted", False))) for n, d in g.nodes(data=True)},
+            {(u, v): (d["visits"], round(d["reward"], 9)) for u, v, d in g.edges(data=True)})
+
+
+@pytest.mark.parametrize("comps,regs,kw", [("ABC", "DE", {}), ("ABCD", "E", {}), ("ABC", "", {"max_interactions_per_promoter": 3})])
+def test_native_dimers_delta_merge_equals_single_tree_sums(comps, regs, kw):
+    """Replica exchange on DimersGrammar trees: their keys are process-local ids of interned interaction lists, so
+    the lists themselves travel (1 + ceil((cap - 6) / 7) words per state).  After exchanging, every replica holds the
+    sum of all replicas' increments, by state string, although the three processes interned their states in
+    different orders."""
+    root = comps + "+" + regs + "::"
+    reps = [NativeTree(dimers_grammar(comps, regs, **kw), root, seed=s, n_exhausted=np.inf, reward_fn=crc_rewards) for s in (1, 2, 3)]
+    solo = [NativeTree(dimers_grammar(comps, regs, **kw), root, seed=s, n_exhausted=np.inf, reward_fn=crc_rewards) for s in (1, 2, 3)]
+    for r, t in zip(reps, solo):
+        r.search_mcts(300, batch_size=16)
+        t.search_mcts(300, batch_size=16)
+    bufs = [r.pack_deltas().copy() for r in reps]
+    d = NativeTree.unpack_deltas(bufs[0])
+    cap = min(reps[0].grammar.max_interactions, reps[0].grammar.max_interactions_per_promoter * len(comps))
+    assert d["key_words"] == 1 + max(0, -(-(cap - 6) // 7)) == (1 if comps == "ABC" and regs else 2)
+    assert d["node_key"].size == len(d["node_dv"]) * d["key_words"]
+    for i, r in enumerate(reps):
+        for j, b in enumerate(bufs):
+            if i != j:
+                assert r.merge_packed(b) is False
+    # expected: the three independent searches added up, state by state
+    want_n, want_e = {}, {}
+    for t in solo:
+        n, e = _node_stats(t)
+        for k, (v, w, _) in n.items():
+            a = want_n.get(k, (0, 0.0))
+            want_n[k] = (a[0] + v, a[1] + w)
+        for k, (v, w) in e.items():
+            a = want_e.get(k, (0, 0.0))
+            want_e[k] = (a[0] + v, a[1] + w)
+    for r in reps:
+        n, e = _node_stats(r)
+        assert set(n) == set(want_n) and set(e) == set(want_e)
+        assert all(n[k][0] == want_n[k][0] and abs(n[k][1] - want_n[k][1]) < 1e-6 for k in n)
+        assert all(e[k][0] == want_e[k][0] and abs(e[k][1] - want_e[k][1]) < 1e-6 for k in e)
+    assert reps[0].to_networkx().nodes[root]["visits"] == 900
+    # nothing is sent twice, and a search continues on the merged tree
+    assert len(NativeTree.unpack_deltas(reps[0].pack_deltas())["node_dv"]) == 0
+    reps[0].search_mcts(50, batch_size=8)
+    assert reps[0].to_networkx().nodes[root]["visits"] == 950
+
+
+def test_native_dimers_exchange_with_finite_n_exhausted_and_foreign_buffers():
+    """Exhaustion events travel as interaction lists too; replicas agree state by state and end exhausted.  A buffer
+    of another grammar (other key width) or a malformed list is refused without touching the tree."""
+    from circuitree_b200 import _capi
+
+    mk = lambda s: NativeTree(dimers_grammar("AB", "R"), "AB+R::", seed=20 + s, n_exhausted=2, reward_fn=crc_rewards)
+    reps = [mk(0), mk(1)]
+    exhausted = [False, False]
+    rounds = 0
+    while not all(exhausted) and rounds < 3000:
+        for i, r in enumerate(reps):
+            if not exhausted[i]:
+                try:
+                    r.search_mcts(64, batch_size=8)
+                except NativeExhaustionError:
+                    exhausted[i] = True
+        bufs = [r.pack_deltas().copy() for r in reps]
+        for i, r in enumerate(reps):
+            if r.merge_packed(bufs[1 - i]):
+                exhausted[i] = True
+        rounds += 1
+        (n0, _), (n1, _) = _node_stats(reps[0]), _node_stats(reps[1])
+        assert {k: (v[0], v[2]) for k, v in n0.items()} == {k: (v[0], v[2]) for k, v in n1.items()}, rounds
+        assert all(v[0] >= 0 for v in n0.values())
+    assert all(exhausted) and rounds > 1
+    assert reps[0].to_networkx().nodes["AB+R::"].get("is_exhausted")
+    # foreign / malformed buffers
+    simple = native(3, "ABC::", 1)
+    simple.search_mcts(20)
+    wide = NativeTree(dimers_grammar("ABCD", "E"), "ABCD+E::", seed=1, reward_fn=crc_rewards)
+    wide.search_mcts(20)
+    before = _node_stats(wide)
     with pytest.raises(_capi.EngineError):
-        t.pack_deltas()                                                                             # process-local keys
+        wide.merge_packed(simple.pack_deltas())                 # one word per key vs two
+    buf = NativeTree(dimers_grammar("ABCD", "E"), "ABCD+E::", seed=2, reward_fn=crc_rewards)
+    buf.search_mcts(20)
+    b = buf.pack_deltas().copy()
+    d = NativeTree.unpack_deltas(b)
+    assert d["key_words"] == 2
+    x = int(np.argmax((d["node_key"][:, 0] >> np.uint64(1)) & np.uint64(127)))      # a state with >= 1 interaction
+    b[NativeTree.PACK_HEADER + 2 * x] |= np.int64(511) << np.int64(8)                # code 511 does not exist
+    with pytest.raises(_capi.EngineError):
+        wide.merge_packed(b)
+    assert _node_stats(wide) == before

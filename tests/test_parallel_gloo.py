@@ -21,8 +21,14 @@ WORKER = textwrap.dedent("""
     crc = lambda states: [(zlib.crc32(s.encode()) %% 1000) / 1000.0 for s in states]
     n_exh = float(os.environ["CT_TEST_NEXH"])
     max_ixn = int(os.environ["CT_TEST_MAXIXN"])
-    tree = NativeTree(SimpleNetworkGrammar(list("ABC"), ["activates", "inhibits"], max_interactions=max_ixn), "ABC::",
-                      seed=100 + rank, n_exhausted=n_exh, reward_fn=crc)
+    ROOT_STATE = os.environ.get("CT_TEST_ROOT", "ABC::")
+    if "+" in ROOT_STATE:       # DimersGrammar: components + regulators
+        from circuitree_b200 import DimersGrammar
+        comps, regs = ROOT_STATE[:-2].split("+")
+        grammar = DimersGrammar(components=list(comps), regulators=list(regs), interactions=["activates", "inhibits"])
+    else:
+        grammar = SimpleNetworkGrammar(list("ABC"), ["activates", "inhibits"], max_interactions=max_ixn)
+    tree = NativeTree(grammar, ROOT_STATE, seed=100 + rank, n_exhausted=n_exh, reward_fn=crc)
     search = RootParallelSearch(tree, sync_every=64, batch_size=16, pipeline_depth=int(os.environ["CT_TEST_DEPTH"]))
     n_done = search.run(int(os.environ["CT_TEST_STEPS"]))
     g = tree.to_networkx()
@@ -32,21 +38,21 @@ WORKER = textwrap.dedent("""
     for u, v in sorted(g.edges):
         h.update(f"{u}>{v}|{g.edges[u, v]['visits']}|{g.edges[u, v]['reward']:.9f}\\n".encode())
     ex = tree.export()
-    out = {"rank": rank, "root_visits": g.nodes["ABC::"]["visits"], "digest": h.hexdigest(), "syncs": search.n_syncs,
+    out = {"rank": rank, "root_visits": g.nodes[ROOT_STATE]["visits"], "digest": h.hexdigest(), "syncs": search.n_syncs,
            "nodes": g.number_of_nodes(), "bytes": search.bytes_exchanged, "n_done": n_done, "exhausted": search.exhausted,
            "min_visits": int(min(ex["node_visits"].min(), ex["edge_visits"].min())),
            "n_flagged": int(ex["node_exhausted"].sum()),
-           "edge_sum": sum(g.edges["ABC::", c]["visits"] for c in g.successors("ABC::"))}
+           "edge_sum": sum(g.edges[ROOT_STATE, c]["visits"] for c in g.successors(ROOT_STATE))}
     open(os.path.join(os.environ["CT_TEST_OUT"], f"rank{rank}.json"), "w").write(json.dumps(out))
     dist.destroy_process_group()
 """) % str(ROOT)
 
 
-def run_world2(tmp_path, port, n_exhausted="inf", max_ixn=9, steps=256, depth=1):
+def run_world2(tmp_path, port, n_exhausted="inf", max_ixn=9, steps=256, depth=1, root="ABC::"):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1", CT_TEST_OUT=str(tmp_path), CT_TEST_NEXH=str(n_exhausted),
-               CT_TEST_MAXIXN=str(max_ixn), CT_TEST_STEPS=str(steps), CT_TEST_DEPTH=str(depth))
+               CT_TEST_MAXIXN=str(max_ixn), CT_TEST_STEPS=str(steps), CT_TEST_DEPTH=str(depth), CT_TEST_ROOT=root)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), str(script)]
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
@@ -77,3 +83,12 @@ def test_root_parallel_merge_world2_finite_n_exhausted(tmp_path):
     assert a["min_visits"] >= 0 and b["min_visits"] >= 0
     assert a["digest"] == b["digest"] and a["n_flagged"] == b["n_flagged"] == a["nodes"]
     assert 0 < a["n_done"] < 64 * 400
+
+
+def test_root_parallel_merge_world2_dimers_grammar(tmp_path):
+    """The same exchange on DimersGrammar trees (five TFs): node keys are process-local there, so the interaction
+    lists travel; both replicas end with the sum of both ranks' work, state by state."""
+    a, b = run_world2(tmp_path, 29521, depth=2, root="ABCD+E::")
+    assert a["root_visits"] == b["root_visits"] == 512 and a["edge_sum"] == 512
+    assert a["digest"] == b["digest"] and a["nodes"] == b["nodes"] > 100
+    assert a["syncs"] == b["syncs"] == 4 and a["bytes"] > 0
