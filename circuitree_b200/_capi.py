@@ -88,6 +88,7 @@ def lib() -> ctypes.CDLL:
     L.ct_engine_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]
     L.ct_compile_topology.argtypes = [i32, vp, i32, vp, i32, i32, ctypes.POINTER(u64)]
     L.ct_topology_info.argtypes = [u64, ctypes.POINTER(i32), ctypes.POINTER(i32)]
+    L.ct_check_params.argtypes = [vp, i64, i32]
     L.ct_launch_rewards.argtypes = [vp, vp, vp, vp, vp, i32, ctypes.POINTER(SimConfig), u64, vp, vp, vp, vp, vp, vp, i32]
     L.ct_reduce_jobs.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     L.ct_rewards_host.argtypes = [vp, vp, vp, vp, vp, i32, ctypes.POINTER(SimConfig), u64, vp, vp, vp, vp, vp]
@@ -98,7 +99,7 @@ def lib() -> ctypes.CDLL:
     L.ct_engine_launch_count.argtypes = [vp]
     L.ct_engine_warp_iterations.restype = i64
     L.ct_engine_warp_iterations.argtypes = [vp]
-    for name in ("ct_topology_info", "ct_default_config", "ct_engine_create", "ct_engine_destroy", "ct_engine_info",
+    for name in ("ct_topology_info", "ct_check_params", "ct_default_config", "ct_engine_create", "ct_engine_destroy", "ct_engine_info",
                  "ct_compile_topology", "ct_launch_rewards", "ct_reduce_jobs", "ct_rewards_host",
                  "ct_reward_from_series_host", "ct_rewards_submit", "ct_rewards_wait"):
         getattr(L, name).restype = ctypes.c_int
@@ -144,6 +145,15 @@ def topology_info(handle: int) -> tuple[int, int]:
     nsp, nr = ctypes.c_int32(0), ctypes.c_int32(0)
     check(lib().ct_topology_info(int(handle), ctypes.byref(nsp), ctypes.byref(nr)))
     return int(nsp.value), int(nr.value)
+
+
+def check_params(params: np.ndarray) -> None:
+    """Raise unless every explicit rate is finite and non-negative (``ct_check_params``; the host-buffer entry
+    points apply the same check themselves)."""
+    a = np.ascontiguousarray(params, dtype=np.float32)
+    if a.ndim != 2:
+        raise EngineError("explicit parameters must have shape (trajectories, parameters per trajectory)")
+    check(lib().ct_check_params(a.ctypes.data, a.shape[0], a.shape[1]))
 
 
 def _ptr(a):

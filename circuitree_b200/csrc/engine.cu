@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <array>
+#include <future>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -144,6 +145,39 @@ int prepare_kernel(KernelInfo& ki)
                                                           ki.smem));
     if (ki.blocks_per_sm < 1) return fail(CT_ERR_CUDA, "SSA kernel (M=%d) does not fit on an SM", MM);
     return CT_OK;
+}
+
+// Explicit parameter vectors must be finite and non-negative: with a NaN or infinite rate the clock of a trajectory
+// never reaches the next grid point and the kernel would never end.  Checked where the buffer is on the host
+// (ct_rewards_host, ct_rewards_submit); a device buffer handed to ct_launch_rewards is the caller's responsibility.
+// Big buffers are scanned by eight threads (168 MB for 2^22 trajectories: ~10 ms against a 2.6 s launch).
+int check_host_params(const float* p, size_t n_traj, size_t np)
+{
+    const size_t n = n_traj * np;
+    auto scan = [](const float* q, size_t m) -> bool {
+        bool bad = false;
+        for (size_t i = 0; i < m; ++i) bad |= !(q[i] >= 0.0f && q[i] <= 3.0e38f);
+        return bad;
+    };
+    bool bad = false;
+    constexpr size_t kSerial = (size_t)1 << 20;
+    if (n <= kSerial) {
+        bad = scan(p, n);
+    } else {
+        constexpr int kThreadsScan = 8;
+        std::future<bool> parts[kThreadsScan];
+        const size_t len = (n + kThreadsScan - 1) / kThreadsScan;
+        for (int x = 0; x < kThreadsScan; ++x) {
+            const size_t a = (size_t)x * len, b = a + len < n ? a + len : n;
+            parts[x] = std::async(std::launch::async, scan, p + (a < n ? a : n), b > a ? b - a : 0);
+        }
+        for (auto& f : parts) bad = f.get() || bad;
+    }
+    if (!bad) return CT_OK;
+    size_t i = 0;
+    while (i < n && p[i] >= 0.0f && p[i] <= 3.0e38f) ++i;
+    return fail(CT_ERR_INVALID, "explicit parameter %zu of trajectory %zu is %g: rates must be finite and non-negative",
+                i % np, i / np, (double)p[i]);
 }
 
 int validate_cfg(const ct_sim_config* cfg)
@@ -373,6 +407,13 @@ int ct_compile_topology(int32_t n_species, const int64_t* act, int32_t n_act, co
     }
     *handle = code;
     return CT_OK;
+}
+
+int ct_check_params(const float* h_params, int64_t n_trajectories, int32_t n_params)
+{
+    if (n_trajectories < 0 || n_params < 1 || n_params > CT_MAX_PARAMS || (n_trajectories && !h_params))
+        return fail(CT_ERR_INVALID, "bad arguments");
+    return check_host_params(h_params, (size_t)n_trajectories, (size_t)n_params);
 }
 
 int ct_topology_info(uint64_t handle, int32_t* n_species, int32_t* n_reactions)
@@ -714,6 +755,7 @@ int ct_rewards_host(ct_engine* eng, const uint64_t* handles, const uint32_t* n_t
     double* d_mean = nullptr;
     uint64_t* d_jev = nullptr;
     int rc;
+    if (h_params && (rc = check_host_params(h_params, (size_t)total, (size_t)params_per_trajectory(handles, n_jobs))) != CT_OK) return rc;
     {
         StreamScratch scratch(s);       // freed in stream order at the end of this block, on every path
         CT_CUDA(scratch.alloc(&d_reward, sizeof(float) * total));
@@ -798,6 +840,10 @@ int ct_rewards_submit(ct_engine* eng, const uint64_t* handles, const uint32_t* n
     t.n_jobs = n_jobs;
     for (int j = 0; j < n_jobs; ++j) t.total += n_traj[j];
     if (t.total == 0) return fail(CT_ERR_INVALID, "empty batch");
+    if (h_params) {
+        const int rcp = check_host_params(h_params, (size_t)t.total, (size_t)params_per_trajectory(handles, n_jobs));
+        if (rcp != CT_OK) return rcp;
+    }
     CT_CUDA(cudaStreamCreateWithFlags(&t.stream, cudaStreamNonBlocking));
     cudaStream_t s = t.stream;
     int rc = submit_on_stream(eng, t, handles, n_traj, traj_base, job_cost, n_jobs, cfg, seed, h_params);

@@ -90,6 +90,11 @@ int ct_compile_topology(int32_t n_species, const int64_t *act, int32_t n_act,
  * per-step work I_step that bench.py's roofline uses (SPEC.md section 8). */
 int ct_topology_info(uint64_t handle, int32_t *n_species, int32_t *n_reactions);
 
+/* The check ct_rewards_host / ct_rewards_submit apply to explicit parameter vectors (host float32
+ * [n_trajectories][n_params]): CT_ERR_INVALID unless every value is finite and non-negative.  A caller that fills
+ * the device buffer of ct_launch_rewards itself can run it on its host copy first.  Needs no GPU. */
+int ct_check_params(const float *h_params, int64_t n_trajectories, int32_t n_params);
+
 /*
  * Device-buffer launch.  Job j simulates n_traj[j] trajectories of topology handles[j]; its
  * trajectory ids are traj_base[j] .. traj_base[j]+n_traj[j]-1 and its outputs occupy the slots
@@ -119,7 +124,9 @@ int ct_reduce_jobs(ct_engine *eng, const uint32_t *n_traj, int32_t n_jobs, void 
  * Host-buffer convenience used by get_reward / get_rewards: copies the job table in, runs
  * the kernel and the per-job reduction, copies job_mean[n_jobs] (float64), job_events[n_jobs]
  * (uint64, nullable) and optionally the per-trajectory reward / lag arrays (host, nullable)
- * back.  Synchronous.
+ * back.  Synchronous.  h_params (nullable: sample per trajectory, SPEC.md section 4) holds CT_N_PARAMS
+ * (CT_N_PARAMS_DIMER) float32 per trajectory; every value must be finite and non-negative, else CT_ERR_INVALID
+ * (a NaN or infinite rate would stall the simulated clock).  ct_launch_rewards does not check its device buffer.
  */
 int ct_rewards_host(ct_engine *eng, const uint64_t *handles, const uint32_t *n_traj,
                     const uint64_t *traj_base, const float *job_cost, int32_t n_jobs,

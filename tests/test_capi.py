@@ -115,3 +115,22 @@ def test_fast_loop_instruction_budget():
     n = int(head.split("point): ")[1].split()[0])
     assert 227 <= n <= 290, head          # 227 = 2 x I_step: fewer would mean the walk lost the path
     assert "MUFU 4" in out.splitlines()[3] and "IMAD 21" in out.splitlines()[3]      # 2 x (lg2 + rcp), Philox + 1
+
+
+def test_explicit_parameters_must_be_finite_and_non_negative():
+    """A NaN, infinite or negative rate would stall a trajectory's clock (a kernel that never ends): the host-buffer
+    entry points refuse such parameter vectors with CT_ERR_INVALID; the check itself needs no GPU."""
+    rg = np.random.default_rng(0)
+    ok = rg.random((1 << 18, 10), dtype=np.float32)            # 2.6 M values: the multi-threaded scan
+    _capi.check_params(ok)
+    _capi.check_params(np.zeros((0, 10), dtype=np.float32))
+    for bad_value in (np.nan, np.inf, -1.0e-3):
+        for where in ((0, 0), (7, 3), ((1 << 18) - 1, 9), (200_000, 5)):
+            bad = ok.copy()
+            bad[where] = bad_value
+            with pytest.raises(_capi.EngineError, match=f"parameter {where[1]} of trajectory {where[0]} "):
+                _capi.check_params(bad)
+    small = np.ones((3, 12), dtype=np.float32)
+    small[2, 11] = np.nan
+    with pytest.raises(_capi.EngineError, match="parameter 11 of trajectory 2 "):
+        _capi.check_params(small)

@@ -343,6 +343,10 @@ def test_error_codes(eng, cfg):
         eng.rewards_host([handle_of("*AB::ABi")], [4], [0], bad, 1)
     with pytest.raises(_capi.EngineError):
         eng.rewards_host([12345], [4], [0], cfg, 1)                    # not a compiled handle (0 species)
+    params = np.full((4, _capi.N_PARAMS), 0.1, dtype=np.float32)
+    params[2, 3] = np.nan                                              # would stall the clock of trajectory 2
+    with pytest.raises(_capi.EngineError, match="parameter 3 of trajectory 2"):
+        eng.rewards_host([handle_of("*AB::ABi")], [4], [0], cfg, 1, params=params)
 
 
 # ---- the reference-facing API ---------------------------------------------------------------------------
