@@ -92,7 +92,10 @@ int ct_topology_info(uint64_t handle, int32_t *n_species, int32_t *n_reactions);
 
 /* The check ct_rewards_host / ct_rewards_submit apply to explicit parameter vectors (host float32
  * [n_trajectories][n_params]): CT_ERR_INVALID unless every value is finite and non-negative.  A caller that fills
- * the device buffer of ct_launch_rewards itself can run it on its host copy first.  Needs no GPU. */
+ * the device buffer of ct_launch_rewards itself can run it on its host copy first.  Needs no GPU.
+ * Not checked: magnitude.  A launch lasts as long as its longest trajectory, and the clock is float32: rates
+ * that put more than ~10^6 events into one grid interval dt make a trajectory arbitrarily slow (SPEC.md's ranges
+ * give 10^1..10^3). */
 int ct_check_params(const float *h_params, int64_t n_trajectories, int32_t n_params);
 
 /*
